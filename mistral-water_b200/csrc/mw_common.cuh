@@ -1,0 +1,93 @@
+// mw_common.cuh -- shared helpers for libmistral_ocean.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <atomic>
+
+#include "../../include/mistral_ocean.h"
+
+// ---------------------------------------------------------------------------------------------
+// error plumbing: thread-local message, negative status codes, no exceptions across the ABI
+// ---------------------------------------------------------------------------------------------
+void mw_set_error(const char* fmt, ...);
+extern std::atomic<long long> g_mw_launches;
+
+#define MW_CUDA(expr)                                                                              \
+    do {                                                                                           \
+        cudaError_t _e = (expr);                                                                   \
+        if (_e != cudaSuccess) {                                                                   \
+            mw_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return (_e == cudaErrorMemoryAllocation) ? MW_E_OOM : MW_E_CUDA;                       \
+        }                                                                                          \
+    } while (0)
+
+#define MW_LAUNCH_CHECK()                                                                          \
+    do {                                                                                           \
+        g_mw_launches.fetch_add(1, std::memory_order_relaxed);                                     \
+        cudaError_t _e = cudaGetLastError();                                                       \
+        if (_e != cudaSuccess) {                                                                   \
+            mw_set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return MW_E_CUDA;                                                                      \
+        }                                                                                          \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// constants of the reference (Scripts/FFTMesh.cs:50-54)
+// ---------------------------------------------------------------------------------------------
+#define MW_PI_F 3.1415926536f
+#define MW_G_F 9.81f
+#define MW_EPSILON_F 0.0001f
+
+// ---------------------------------------------------------------------------------------------
+// complex arithmetic on float2
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 cmul(float2 a, float2 b)
+{
+    return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
+}
+__device__ __forceinline__ float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
+
+// streaming (read-once / write-once) global accesses: keep them out of L1
+__device__ __forceinline__ float4 ldg_stream4(const float4* p)
+{
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ float2 ldg_stream2(const float2* p)
+{
+    float2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al., SC'11), the engine's stand-in for UnityEngine.Random.value.
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                       uint32_t k0, uint32_t k1, uint32_t out[4])
+{
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+        const uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        const uint32_t n1 = (uint32_t)p1;
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        const uint32_t n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+// 24-bit uniform in (0, 1]
+__host__ __device__ __forceinline__ float u32_to_unit_open0(uint32_t u)
+{
+    return (float)((u >> 8) + 1u) * (1.0f / 16777216.0f);
+}

@@ -1,0 +1,150 @@
+// mw_fft2d.cu -- the engine's 2-D transform exposed on caller data (mw_fft2d in mistral_ocean.h).
+//
+// Functionally this is the reference's Stockham blit chain (Shaders/FFT/Stockham.shader:31-57,
+// Scripts/OceanRenderer.cs:229-262: log2 N horizontal radix-2 stages, then log2 N vertical ones) on
+// one complex field: sign = -1 reproduces it; sign = +1 is the conjugate transform the FFTMesh
+// synthesis uses.  It shares mwfft::fft_line with the ocean kernels, so a parity check of this entry
+// point against numpy / the literal stage-by-stage restatement pins the FFT core itself.
+#include <vector>
+#include "mw_fft.cuh"
+
+namespace {
+
+using mwfft::Plan;
+using mwfft::pad_idx;
+
+// LR lines (rows) per CTA, contiguous along the transform direction.
+template <int N, int LR, int SIGN>
+__global__ void __launch_bounds__(LR * (N / 32)) k_fft_rows(const float2* __restrict__ in, float2* __restrict__ out,
+                                                           const float2* __restrict__ tw, int rows_total)
+{
+    using P = Plan<N>;
+    constexpr int T = P::T;
+    extern __shared__ float2 smem[];
+    const int lr = threadIdx.x / T, g = threadIdx.x % T;
+    const int row = blockIdx.x * LR + lr;
+    const bool active = row < rows_total;
+    float2* line = smem + lr * P::PITCH;
+    if (active) {
+        const float2* src = in + (size_t)row * N;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) line[pad_idx(g + T * c)] = src[g + T * c];
+    }
+    __syncthreads();
+    float2* dst = out + (size_t)row * N;
+    mwfft::fft_line<N, SIGN>(line, g, active, tw, [&](int idx, float2 v) { dst[idx] = v; });
+}
+
+// Slab of W columns per CTA: transposing load, FFT along the strided direction, transposing store.
+template <int N, int W, int SIGN>
+__global__ void __launch_bounds__(W * (N / 32)) k_fft_cols(const float2* __restrict__ in, float2* __restrict__ out,
+                                                          const float2* __restrict__ tw)
+{
+    using P = Plan<N>;
+    constexpr int T = P::T;
+    constexpr int MAIN = W * T;
+    extern __shared__ float2 smem[];
+    const int tid = threadIdx.x;
+    const int q = tid / T, g = tid % T;
+    const int b0 = blockIdx.x * W;
+    const size_t base = (size_t)blockIdx.y * N * N;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+        const int e = tid + k * MAIN;
+        smem[(e % W) * P::PITCH + pad_idx(e / W)] = in[base + (size_t)(e / W) * N + b0 + (e % W)];
+    }
+    __syncthreads();
+    float2* line = smem + q * P::PITCH;
+    mwfft::fft_line<N, SIGN>(line, g, true, tw, [&](int idx, float2 v) { line[pad_idx(idx)] = v; });
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+        const int e = tid + k * MAIN;
+        out[base + (size_t)(e / W) * N + b0 + (e % W)] = smem[(e % W) * P::PITCH + pad_idx(e / W)];
+    }
+}
+
+template <int N, int SIGN>
+int run2d(int batch, const float2* d_in, float2* d_tmp, float2* d_out, const float2* d_tw, cudaStream_t st)
+{
+    constexpr int T = N / 32;
+    constexpr int LR = (T >= 32) ? 4 : (128 / T);
+    constexpr int W = 8;
+    constexpr size_t smem_r = (size_t)LR * Plan<N>::PITCH * sizeof(float2);
+    constexpr size_t smem_c = (size_t)W * Plan<N>::PITCH * sizeof(float2);
+    MW_CUDA(cudaFuncSetAttribute(k_fft_rows<N, LR, SIGN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r));
+    MW_CUDA(cudaFuncSetAttribute(k_fft_cols<N, W, SIGN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
+    const int rows_total = batch * N;
+    k_fft_rows<N, LR, SIGN><<<(rows_total + LR - 1) / LR, LR * T, smem_r, st>>>(d_in, d_tmp, d_tw, rows_total);
+    MW_LAUNCH_CHECK();
+    k_fft_cols<N, W, SIGN><<<dim3(N / W, batch), W * T, smem_c, st>>>(d_tmp, d_out, d_tw);
+    MW_LAUNCH_CHECK();
+    return MW_OK;
+}
+
+template <int SIGN>
+int dispatch(int n, int batch, const float2* d_in, float2* d_tmp, float2* d_out, const float2* d_tw, cudaStream_t st)
+{
+    switch (n) {
+        case 32: return run2d<32, SIGN>(batch, d_in, d_tmp, d_out, d_tw, st);
+        case 64: return run2d<64, SIGN>(batch, d_in, d_tmp, d_out, d_tw, st);
+        case 128: return run2d<128, SIGN>(batch, d_in, d_tmp, d_out, d_tw, st);
+        case 256: return run2d<256, SIGN>(batch, d_in, d_tmp, d_out, d_tw, st);
+        case 512: return run2d<512, SIGN>(batch, d_in, d_tmp, d_out, d_tw, st);
+        case 1024: return run2d<1024, SIGN>(batch, d_in, d_tmp, d_out, d_tw, st);
+        case 2048: return run2d<2048, SIGN>(batch, d_in, d_tmp, d_out, d_tw, st);
+    }
+    mw_set_error("mw_fft2d: n must be a power of two in [32, 2048], got %d", n);
+    return MW_E_INVALID_ARG;
+}
+
+}  // namespace
+
+extern "C" int mw_fft2d(int device, int32_t n, int32_t batch, int sign, const float* in, float* out)
+{
+    if (!in || !out || batch < 1 || (sign != 1 && sign != -1)) {
+        mw_set_error("mw_fft2d: bad argument (null buffer, batch < 1 or sign not +-1)");
+        return MW_E_INVALID_ARG;
+    }
+    if (n < 32 || n > 2048 || (n & (n - 1))) {
+        mw_set_error("mw_fft2d: n must be a power of two in [32, 2048], got %d", n);
+        return MW_E_INVALID_ARG;
+    }
+    MW_CUDA(cudaSetDevice(device));
+    const size_t total = (size_t)batch * n * n;
+    float2 *d_a = nullptr, *d_b = nullptr, *d_tw = nullptr;
+    std::vector<float2> tw(n);
+    const double PI_D = 3.14159265358979323846;
+    for (int x = 0; x < n; ++x) tw[x] = make_float2((float)cos(2.0 * PI_D * x / n), (float)sin(2.0 * PI_D * x / n));
+    int rc = MW_OK;
+    cudaStream_t st = nullptr;
+    auto cleanup = [&]() {
+        if (d_a) cudaFree(d_a);
+        if (d_b) cudaFree(d_b);
+        if (d_tw) cudaFree(d_tw);
+        if (st) cudaStreamDestroy(st);
+    };
+#define MW_TRY(expr)                                                                                   \
+    do {                                                                                               \
+        cudaError_t _e = (expr);                                                                       \
+        if (_e != cudaSuccess) {                                                                       \
+            mw_set_error("%s failed: %s", #expr, cudaGetErrorString(_e));                              \
+            cleanup();                                                                                 \
+            return _e == cudaErrorMemoryAllocation ? MW_E_OOM : MW_E_CUDA;                             \
+        }                                                                                              \
+    } while (0)
+    MW_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    MW_TRY(cudaMalloc((void**)&d_a, total * sizeof(float2)));
+    MW_TRY(cudaMalloc((void**)&d_b, total * sizeof(float2)));
+    MW_TRY(cudaMalloc((void**)&d_tw, n * sizeof(float2)));
+    MW_TRY(cudaMemcpyAsync(d_tw, tw.data(), n * sizeof(float2), cudaMemcpyHostToDevice, st));
+    MW_TRY(cudaMemcpyAsync(d_a, in, total * sizeof(float2), cudaMemcpyHostToDevice, st));
+    // rows: a -> b ; columns: b -> a
+    rc = sign > 0 ? dispatch<+1>(n, batch, d_a, d_b, d_a, d_tw, st) : dispatch<-1>(n, batch, d_a, d_b, d_a, d_tw, st);
+    if (rc == MW_OK) {
+        MW_TRY(cudaMemcpyAsync(out, d_a, total * sizeof(float2), cudaMemcpyDeviceToHost, st));
+        MW_TRY(cudaStreamSynchronize(st));
+    }
+    cleanup();
+    return rc;
+}

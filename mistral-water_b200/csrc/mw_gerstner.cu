@@ -1,0 +1,179 @@
+// mw_gerstner.cu -- pond renderer: Gerstner sum-of-waves vertex displacement (sm_100a).
+//
+// Replaces the per-vertex work of Shaders/MistralWaterLib.cginc Gerstner (:71-99) /
+// GerstnerLevelOne (:101-125) as dispatched by Displacement (:154-180), generalised to a W-wave
+// table (both reference variants are special cases; see mw_gerstner_from_material /
+// mw_gerstner_append_level_one).
+//
+// Roofline note: 24 B/vertex of traffic against 2 transcendentals + ~12 flops per
+// wave; at W = 32 this kernel is bound by the MUFU/FP32 pipes, not by HBM.
+#include <string.h>
+#include "mw_common.cuh"
+
+namespace {
+
+struct GerstnerTable {
+    int n_waves;
+    mw_gerstner_wave w[MW_GERSTNER_MAX_WAVES];
+};
+
+// sin/cos of an fp32 phase: explicit 3-term Cody-Waite reduction to [-pi, pi] followed by the
+// MUFU approximations (abs. error ~5e-7 on the reduced range).  |theta| stays far below 2^17 here.
+__device__ __forceinline__ void sincos_reduced(float th, float* s, float* c)
+{
+    const float k = rintf(th * 0.15915494309189535f);  // theta / 2pi
+    float r = fmaf(k, -6.28125f, th);                  // 2pi = 6.28125 + 1.9350051879882812e-3 + 3.019916050561733e-7
+    r = fmaf(k, -1.9350051879882812e-3f, r);
+    r = fmaf(k, -3.019916050561733e-7f, r);
+    *s = __sinf(r);
+    *c = __cosf(r);
+}
+
+constexpr int VPT = 4;  // vertices per thread: 3 float4 in, 3 float4 out
+constexpr int THREADS = 256;
+
+template <bool NRM>
+__global__ void __launch_bounds__(THREADS) k_gerstner(const __grid_constant__ GerstnerTable tab, const float* __restrict__ pos,
+                                                      float* __restrict__ out, float* __restrict__ nrm, int64_t n, float t)
+{
+    const int64_t v0 = ((int64_t)blockIdx.x * THREADS + threadIdx.x) * VPT;
+    if (v0 >= n) return;
+    float p[VPT * 3];
+    const bool full = v0 + VPT <= n;
+    if (full) {
+        const float4* src = reinterpret_cast<const float4*>(pos + 3 * v0);  // 48-byte aligned: v0 % 4 == 0
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const float4 q = ldg_stream4(src + k);
+            p[4 * k + 0] = q.x; p[4 * k + 1] = q.y; p[4 * k + 2] = q.z; p[4 * k + 3] = q.w;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < VPT * 3; ++k) p[k] = (3 * v0 + k < 3 * n) ? pos[3 * v0 + k] : 0.f;
+    }
+    float ox[VPT], oy[VPT], oz[VPT];
+#pragma unroll
+    for (int v = 0; v < VPT; ++v) ox[v] = oy[v] = oz[v] = 0.f;
+    const int nw = tab.n_waves;
+#pragma unroll 2
+    for (int w = 0; w < nw; ++w) {
+        const mw_gerstner_wave W = tab.w[w];
+        const float ph = W.rate * t;  // speeds * t   (MistralWaterLib.cginc:81, :114)
+        const float ax = W.amp_xz * W.dir_x, az = W.amp_xz * W.dir_y;
+#pragma unroll
+        for (int v = 0; v < VPT; ++v) {
+            // theta = freq * dot(dir, sVertex.xz) + rate * t   (:80-84, :114-116)
+            const float d = W.dir_x * p[3 * v + 0] + W.dir_y * p[3 * v + 2];
+            const float th = fmaf(W.freq, d, ph);
+            float s, c;
+            sincos_reduced(th, &s, &c);
+            ox[v] = fmaf(ax, c, ox[v]);       // :86 / :114
+            oz[v] = fmaf(az, c, oz[v]);       // :87 / :115
+            oy[v] = fmaf(W.amp_y, s, oy[v]);  // :88 / :116
+        }
+    }
+#pragma unroll
+    for (int v = 0; v < VPT; ++v) { p[3 * v + 0] += ox[v]; p[3 * v + 1] += oy[v]; p[3 * v + 2] += oz[v]; }  // :176
+    if (full) {
+        float4* dst = reinterpret_cast<float4*>(out + 3 * v0);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) dst[k] = make_float4(p[4 * k + 0], p[4 * k + 1], p[4 * k + 2], p[4 * k + 3]);
+        if (NRM) {  // (0,1,0) x4 = 0 1 0 0 | 1 0 0 1 | 0 0 1 0   (:98, :121)
+            float4* dn = reinterpret_cast<float4*>(nrm + 3 * v0);
+            dn[0] = make_float4(0.f, 1.f, 0.f, 0.f);
+            dn[1] = make_float4(1.f, 0.f, 0.f, 1.f);
+            dn[2] = make_float4(0.f, 0.f, 1.f, 0.f);
+        }
+    } else {
+        for (int k = 0; k < VPT * 3; ++k)
+            if (3 * v0 + k < 3 * n) {
+                out[3 * v0 + k] = p[k];
+                if (NRM) nrm[3 * v0 + k] = (k % 3 == 1) ? 1.f : 0.f;
+            }
+    }
+}
+
+}  // namespace
+
+extern "C" int mw_gerstner_from_material(mw_gerstner_params* p, float amplitude, float frequency, float steepness,
+                                         const float w_speed[4], const float w_direction_ab[4], const float w_direction_cd[4])
+{
+    if (!p || !w_speed || !w_direction_ab || !w_direction_cd) { mw_set_error("null argument"); return MW_E_INVALID_ARG; }
+    const float amp = amplitude * 0.01f;  // MistralWaterLib.cginc:172
+    const float dirs[4][2] = {{w_direction_ab[0], w_direction_ab[1]}, {w_direction_ab[2], w_direction_ab[3]},
+                              {w_direction_cd[0], w_direction_cd[1]}, {w_direction_cd[2], w_direction_cd[3]}};
+    p->n_waves = 4;
+    for (int k = 0; k < 4; ++k) {
+        mw_gerstner_wave& w = p->waves[k];
+        w.dir_x = dirs[k][0]; w.dir_y = dirs[k][1];
+        w.freq = frequency;          // :80
+        w.rate = w_speed[k];         // :81
+        w.amp_xz = steepness * amp;  // :77-78
+        w.amp_y = amp;               // :88
+    }
+    return MW_OK;
+}
+
+extern "C" int mw_gerstner_append_level_one(mw_gerstner_params* p, float amplitude, float frequency, float steepness)
+{
+    if (!p) { mw_set_error("null argument"); return MW_E_INVALID_ARG; }
+    if (p->n_waves < 0 || p->n_waves + 5 > MW_GERSTNER_MAX_WAVES) { mw_set_error("wave table full"); return MW_E_INVALID_ARG; }
+    // MistralWaterLib.cginc:105-109
+    static const float amps[5] = {0.7f, 0.6f, 0.6f, 0.7f, 0.9f};
+    static const float steeps[5] = {0.95f, 0.615f, 0.821f, 0.462f, 0.611f};
+    static const float speeds[5] = {-2.112f, 0.6124f, -0.878f, -3.6234f, 1.f};
+    static const float dir[5][2] = {{1.f, -0.2f}, {-0.9f, 1.f}, {0.2f, 0.2f}, {-1.0f, 0.77f}, {0.99f, -1.145f}};
+    static const float fs[5] = {0.954f, 1.52f, 0.44f, 0.21f, 0.8f};
+    for (int i = 0; i < 5; ++i) {
+        mw_gerstner_wave& w = p->waves[p->n_waves++];
+        w.dir_x = dir[i][0]; w.dir_y = dir[i][1];
+        w.freq = frequency * fs[i];              // :114
+        w.rate = speeds[i] * frequency * fs[i];  // :114
+        w.amp_xz = steepness * amplitude * steeps[i] * amps[i];
+        w.amp_y = amplitude * amps[i];           // :116
+    }
+    return MW_OK;
+}
+
+extern "C" int mw_gerstner_displace(const mw_gerstner_params* p, const float* pos_xyz, float* out_xyz, float* out_nrm,
+                                    int64_t n, float t, void* cuda_stream)
+{
+    if (!p || !pos_xyz || !out_xyz || n < 0) { mw_set_error("mw_gerstner_displace: bad argument"); return MW_E_INVALID_ARG; }
+    if (p->n_waves < 0 || p->n_waves > MW_GERSTNER_MAX_WAVES) { mw_set_error("n_waves out of range"); return MW_E_INVALID_ARG; }
+    if (n == 0) return MW_OK;
+    MW_CUDA(cudaSetDevice(p->device));
+    GerstnerTable tab;
+    tab.n_waves = p->n_waves;
+    memcpy(tab.w, p->waves, sizeof tab.w);
+    const bool dev = (p->flags & MW_DEVICE_PTRS) != 0;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const float* d_pos = pos_xyz;
+    float* d_out = out_xyz;
+    float* d_nrm = out_nrm;
+    float* scratch = nullptr;
+    const size_t bytes = (size_t)n * 3 * sizeof(float);
+    if (!dev) {
+        MW_CUDA(cudaMalloc((void**)&scratch, bytes * (out_nrm ? 3 : 2)));
+        d_pos = scratch; d_out = scratch + 3 * n; d_nrm = out_nrm ? scratch + 6 * n : nullptr;
+        cudaError_t e = cudaMemcpyAsync(scratch, pos_xyz, bytes, cudaMemcpyHostToDevice, st);
+        if (e != cudaSuccess) { cudaFree(scratch); mw_set_error("H2D failed: %s", cudaGetErrorString(e)); return MW_E_CUDA; }
+    } else if ((reinterpret_cast<uintptr_t>(pos_xyz) | reinterpret_cast<uintptr_t>(out_xyz) |
+                reinterpret_cast<uintptr_t>(out_nrm)) & 15) {
+        mw_set_error("device buffers must be 16-byte aligned");
+        return MW_E_INVALID_ARG;
+    }
+    const int64_t threads_needed = (n + VPT - 1) / VPT;
+    const unsigned grid = (unsigned)((threads_needed + THREADS - 1) / THREADS);
+    if (d_nrm) k_gerstner<true><<<grid, THREADS, 0, st>>>(tab, d_pos, d_out, d_nrm, n, t);
+    else k_gerstner<false><<<grid, THREADS, 0, st>>>(tab, d_pos, d_out, nullptr, n, t);
+    g_mw_launches.fetch_add(1, std::memory_order_relaxed);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess && !dev) {
+        e = cudaMemcpyAsync(out_xyz, d_out, bytes, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess && out_nrm) e = cudaMemcpyAsync(out_nrm, d_nrm, bytes, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    }
+    if (scratch) cudaFree(scratch);
+    if (e != cudaSuccess) { mw_set_error("mw_gerstner_displace failed: %s", cudaGetErrorString(e)); return MW_E_CUDA; }
+    return MW_OK;
+}

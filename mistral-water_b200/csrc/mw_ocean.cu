@@ -1,0 +1,476 @@
+// mw_ocean.cu -- handle management and the C ABI of the ocean path (include/mistral_ocean.h).
+#include <math.h>
+#include <string.h>
+#include <new>
+#include <vector>
+
+#include "mw_ocean_kernels.cuh"
+
+// ---------------------------------------------------------------------------------------------
+// error text (thread-local) and global launch counter
+// ---------------------------------------------------------------------------------------------
+static thread_local char t_err[512] = "";
+std::atomic<long long> g_mw_launches{0};
+
+void mw_set_error(const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(t_err, sizeof t_err, fmt, ap);
+    va_end(ap);
+}
+extern "C" const char* mw_last_error(void) { return t_err; }
+extern "C" int mw_version(void) { return MW_VERSION; }
+extern "C" int64_t mw_kernel_launch_count(void) { return (int64_t)g_mw_launches.load(); }
+
+// ---------------------------------------------------------------------------------------------
+// handle
+// ---------------------------------------------------------------------------------------------
+struct EvPair { cudaEvent_t a, b; int kid; };
+
+struct mw_ocean {
+    mw_ocean_params p;
+    int N = 0;
+    int tiles = 1;
+    size_t n2 = 0;
+    bool device_ptrs = false;
+    bool profile = false;
+    bool have_h0 = false;
+    float timer = 0.f;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    // device state
+    float4* spec = nullptr;   // [tiles][N*N] (h0, h0conj)
+    float* omega = nullptr;   // [N*N]
+    float2* ramp = nullptr;   // [2N]
+    float* kd = nullptr;      // [N]
+    float2* tw = nullptr;     // [N]
+    float2* X = nullptr;      // [tiles][3][N*N]
+    // scratch outputs (host-pointer mode, or inputs of k_mesh_outputs)
+    float* s_height = nullptr; float2* s_disp = nullptr; float* s_normal = nullptr; float* s_white = nullptr;
+    float* s_jac = nullptr; float* s_vert = nullptr; float4* s_col = nullptr; float2* s_h = nullptr;
+    // profiling
+    std::vector<EvPair> ev_pool; size_t ev_used = 0;
+    double k_ms[MW_KERNEL_COUNT] = {0, 0, 0};
+    int64_t k_n[MW_KERNEL_COUNT] = {0, 0, 0};
+};
+
+static int drain_events(mw_ocean* o)
+{
+    if (o->ev_used == 0) return MW_OK;
+    MW_CUDA(cudaStreamSynchronize(o->stream));
+    for (size_t i = 0; i < o->ev_used; ++i) {
+        float ms = 0.f;
+        MW_CUDA(cudaEventElapsedTime(&ms, o->ev_pool[i].a, o->ev_pool[i].b));
+        o->k_ms[o->ev_pool[i].kid] += ms;
+        o->k_n[o->ev_pool[i].kid] += 1;
+    }
+    o->ev_used = 0;
+    return MW_OK;
+}
+
+struct ProfScope {
+    mw_ocean* o; EvPair* e = nullptr;
+    ProfScope(mw_ocean* o_, int kid) : o(o_)
+    {
+        if (!o->profile) return;
+        if (o->ev_used == o->ev_pool.size()) {
+            if (o->ev_pool.size() >= 4096) { drain_events(o); }
+            else {
+                EvPair p; p.kid = 0;
+                if (cudaEventCreate(&p.a) != cudaSuccess || cudaEventCreate(&p.b) != cudaSuccess) return;
+                o->ev_pool.push_back(p);
+            }
+        }
+        e = &o->ev_pool[o->ev_used++];
+        e->kid = kid;
+        cudaEventRecord(e->a, o->stream);
+    }
+    ~ProfScope() { if (e) cudaEventRecord(e->b, o->stream); }
+};
+
+template <class T>
+static int ensure(T** p, size_t count)
+{
+    if (*p) return MW_OK;
+    MW_CUDA(cudaMalloc((void**)p, count * sizeof(T)));
+    return MW_OK;
+}
+
+static bool is_pow2(int x) { return x > 0 && (x & (x - 1)) == 0; }
+
+extern "C" int mw_ocean_create(const mw_ocean_params* params, mw_ocean** out)
+{
+    if (!params || !out) { mw_set_error("mw_ocean_create: null argument"); return MW_E_INVALID_ARG; }
+    *out = nullptr;
+    const mw_ocean_params& p = *params;
+    if (!is_pow2(p.resolution) || p.resolution < 32 || p.resolution > 2048) {
+        mw_set_error("resolution must be a power of two in [32, 2048], got %d (no O(N^4) fallback exists)", p.resolution);
+        return MW_E_INVALID_ARG;
+    }
+    if (!(p.unit_width > 0.f) || !(p.length > 0.f) || !isfinite(p.unit_width) || !isfinite(p.length)) {
+        mw_set_error("unit_width and length must be positive and finite");
+        return MW_E_INVALID_ARG;
+    }
+    {
+        const float want = (float)p.resolution * p.unit_width;
+        if (fabsf(p.length - want) > 1e-6f * fabsf(want)) {
+            mw_set_error("length (%g) must equal resolution * unit_width (%g): only the periodic case is an FFT", p.length, want);
+            return MW_E_INVALID_ARG;
+        }
+    }
+    if (p.tiles < 1 || p.tiles > 65535) { mw_set_error("tiles must be in [1, 65535], got %d", p.tiles); return MW_E_INVALID_ARG; }
+    if (!(p.t_division != 0.f)) { mw_set_error("t_division must be non-zero"); return MW_E_INVALID_ARG; }
+    int ndev = 0;
+    MW_CUDA(cudaGetDeviceCount(&ndev));
+    if (p.device < 0 || p.device >= ndev) { mw_set_error("device %d out of range (%d devices)", p.device, ndev); return MW_E_INVALID_ARG; }
+    MW_CUDA(cudaSetDevice(p.device));
+    {
+        cudaDeviceProp prop;
+        MW_CUDA(cudaGetDeviceProperties(&prop, p.device));
+        if (prop.major != 10) {
+            mw_set_error("device %d is sm_%d%d; this library is built for sm_100a (B200) only", p.device, prop.major, prop.minor);
+            return MW_E_CUDA;
+        }
+    }
+    mw_ocean* o = new (std::nothrow) mw_ocean();
+    if (!o) { mw_set_error("out of host memory"); return MW_E_OOM; }
+    o->p = p;
+    o->N = p.resolution;
+    o->tiles = p.tiles;
+    o->n2 = (size_t)o->N * o->N;
+    o->device_ptrs = (p.flags & MW_DEVICE_PTRS) != 0;
+    o->profile = (p.flags & MW_PROFILE) != 0;
+    const int N = o->N;
+    int rc = MW_OK;
+    auto fail = [&](int code) { mw_ocean_destroy(o); return code; };
+    if (cudaStreamCreateWithFlags(&o->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        mw_set_error("cudaStreamCreate failed"); return fail(MW_E_CUDA);
+    }
+    o->stream = o->own_stream;
+    if ((rc = ensure(&o->spec, o->n2 * o->tiles))) return fail(rc);
+    if ((rc = ensure(&o->omega, o->n2))) return fail(rc);
+    if ((rc = ensure(&o->ramp, (size_t)2 * N))) return fail(rc);
+    if ((rc = ensure(&o->kd, (size_t)N))) return fail(rc);
+    if ((rc = ensure(&o->tw, (size_t)N))) return fail(rc);
+    if ((rc = ensure(&o->X, o->n2 * 3 * o->tiles))) return fail(rc);
+
+    // small host-built tables
+    std::vector<float2> tw(N), ramp(2 * N);
+    std::vector<float> kd(N);
+    const double PI_D = 3.14159265358979323846;
+    for (int x = 0; x < N; ++x) tw[x] = make_float2((float)cos(2.0 * PI_D * x / N), (float)sin(2.0 * PI_D * x / N));
+    for (int s = 0; s < 2 * N; ++s) {
+        // exp(i pi s (1 - N) / N), angle reduced exactly: s (N-1) mod 2N
+        const long long u = ((long long)s * (N - 1)) % (2LL * N);
+        ramp[s] = make_float2((float)cos(-PI_D * (double)u / N), (float)sin(-PI_D * (double)u / N));
+    }
+    for (int i = 0; i < N; ++i) {
+        // FFTMesh.cs:201  kx = 2 * PI * (i - resolution / 2.0f) / length   (strict fp32, source order)
+        volatile float two_pi = 2.0f * MW_PI_F;
+        volatile float d = (float)i - (float)N / 2.0f;
+        volatile float num = two_pi * d;
+        kd[i] = num / p.length;
+    }
+    if (cudaMemcpy(o->tw, tw.data(), N * sizeof(float2), cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(o->ramp, ramp.data(), 2 * N * sizeof(float2), cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(o->kd, kd.data(), N * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
+        mw_set_error("table upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return fail(MW_E_CUDA);
+    }
+    mwk::k_dispersion<<<(unsigned)((o->n2 + 255) / 256), 256, 0, o->stream>>>(o->omega, N, p.length);
+    g_mw_launches.fetch_add(1);
+    if (cudaStreamSynchronize(o->stream) != cudaSuccess) {
+        mw_set_error("k_dispersion failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return fail(MW_E_CUDA);
+    }
+    *out = o;
+    return MW_OK;
+}
+
+extern "C" void mw_ocean_destroy(mw_ocean* o)
+{
+    if (!o) return;
+    cudaSetDevice(o->p.device);
+    if (o->stream) cudaStreamSynchronize(o->stream);
+    for (auto& e : o->ev_pool) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+    void* ptrs[] = {o->spec, o->omega, o->ramp, o->kd, o->tw, o->X, o->s_height, o->s_disp, o->s_normal,
+                    o->s_white, o->s_jac, o->s_vert, o->s_col, o->s_h};
+    for (void* q : ptrs) if (q) cudaFree(q);
+    if (o->own_stream) cudaStreamDestroy(o->own_stream);
+    delete o;
+}
+
+#define MW_CHECK_HANDLE(o)                                                         \
+    do {                                                                           \
+        if (!(o)) { mw_set_error("null handle"); return MW_E_INVALID_ARG; }        \
+        MW_CUDA(cudaSetDevice((o)->p.device));                                     \
+    } while (0)
+
+extern "C" int mw_ocean_sync(mw_ocean* o)
+{
+    MW_CHECK_HANDLE(o);
+    MW_CUDA(cudaStreamSynchronize(o->stream));
+    return MW_OK;
+}
+
+extern "C" int mw_ocean_set_stream(mw_ocean* o, void* cuda_stream)
+{
+    MW_CHECK_HANDLE(o);
+    MW_CUDA(cudaStreamSynchronize(o->stream));
+    int rc = drain_events(o);
+    if (rc) return rc;
+    o->stream = cuda_stream ? (cudaStream_t)cuda_stream : o->own_stream;
+    return MW_OK;
+}
+
+extern "C" int mw_ocean_init_spectrum(mw_ocean* o)
+{
+    MW_CHECK_HANDLE(o);
+    const size_t total = o->n2 * o->tiles;
+    mwk::k_init_spectrum<<<(unsigned)((total + 127) / 128), 128, 0, o->stream>>>(
+        o->spec, o->N, o->tiles, o->p.length, o->p.amplitude, o->p.wind_x, o->p.wind_y, o->p.seed);
+    MW_LAUNCH_CHECK();
+    if (!o->device_ptrs) MW_CUDA(cudaStreamSynchronize(o->stream));
+    o->have_h0 = true;
+    return MW_OK;
+}
+
+extern "C" int mw_ocean_set_h0(mw_ocean* o, const float* h0, const float* h0conj)
+{
+    MW_CHECK_HANDLE(o);
+    if (!h0 || !h0conj) { mw_set_error("mw_ocean_set_h0: null buffer"); return MW_E_INVALID_ARG; }
+    const size_t total = o->n2 * o->tiles;
+    const float2 *d0 = (const float2*)h0, *d1 = (const float2*)h0conj;
+    if (!o->device_ptrs) {
+        // stage through X (large enough: 3 float2 per point), then interleave on the device
+        float2* stage = o->X;
+        MW_CUDA(cudaMemcpyAsync(stage, h0, total * sizeof(float2), cudaMemcpyHostToDevice, o->stream));
+        MW_CUDA(cudaMemcpyAsync(stage + total, h0conj, total * sizeof(float2), cudaMemcpyHostToDevice, o->stream));
+        d0 = stage; d1 = stage + total;
+    }
+    mwk::k_pack_h0<<<(unsigned)((total + 255) / 256), 256, 0, o->stream>>>(o->spec, d0, d1, (int64_t)total);
+    MW_LAUNCH_CHECK();
+    if (!o->device_ptrs) MW_CUDA(cudaStreamSynchronize(o->stream));
+    o->have_h0 = true;
+    return MW_OK;
+}
+
+extern "C" int mw_ocean_get_h0(mw_ocean* o, float* h0, float* h0conj)
+{
+    MW_CHECK_HANDLE(o);
+    if (!h0 || !h0conj) { mw_set_error("mw_ocean_get_h0: null buffer"); return MW_E_INVALID_ARG; }
+    if (!o->have_h0) { mw_set_error("h0 not initialised: call mw_ocean_init_spectrum or mw_ocean_set_h0 first"); return MW_E_STATE; }
+    const size_t total = o->n2 * o->tiles;
+    float2 *d0 = (float2*)h0, *d1 = (float2*)h0conj;
+    if (!o->device_ptrs) { d0 = o->X; d1 = o->X + total; }
+    mwk::k_unpack_h0<<<(unsigned)((total + 255) / 256), 256, 0, o->stream>>>(o->spec, d0, d1, (int64_t)total);
+    MW_LAUNCH_CHECK();
+    if (!o->device_ptrs) {
+        MW_CUDA(cudaMemcpyAsync(h0, d0, total * sizeof(float2), cudaMemcpyDeviceToHost, o->stream));
+        MW_CUDA(cudaMemcpyAsync(h0conj, d1, total * sizeof(float2), cudaMemcpyDeviceToHost, o->stream));
+        MW_CUDA(cudaStreamSynchronize(o->stream));
+    }
+    return MW_OK;
+}
+
+extern "C" int mw_ocean_get_rest_vertices(mw_ocean* o, float* xyz)
+{
+    if (!o || !xyz) { mw_set_error("null argument"); return MW_E_INVALID_ARG; }
+    const int N = o->N;
+    const float uw = o->p.unit_width;
+    // FFTMesh.cs:104-112 (resolution is even here)
+    for (int i = 0; i < N; ++i) {
+        volatile float hp = (float)(i - N / 2) * uw;
+        for (int j = 0; j < N; ++j) {
+            volatile float vp = (float)(j - N / 2) * uw;
+            volatile float off = uw / 2.0f;
+            float* v = xyz + 3 * ((size_t)i * N + j);
+            v[0] = hp + off; v[1] = 0.f; v[2] = vp + off;
+        }
+    }
+    return MW_OK;
+}
+
+extern "C" int mw_ocean_get_dispersion(mw_ocean* o, float* omega)
+{
+    MW_CHECK_HANDLE(o);
+    if (!omega) { mw_set_error("null buffer"); return MW_E_INVALID_ARG; }
+    MW_CUDA(cudaMemcpyAsync(omega, o->omega, o->n2 * sizeof(float), cudaMemcpyDeviceToHost, o->stream));
+    MW_CUDA(cudaStreamSynchronize(o->stream));
+    return MW_OK;
+}
+
+extern "C" int mw_ocean_evolve_spectrum(mw_ocean* o, float t, float* htilde)
+{
+    MW_CHECK_HANDLE(o);
+    if (!htilde) { mw_set_error("null buffer"); return MW_E_INVALID_ARG; }
+    if (!o->have_h0) { mw_set_error("h0 not initialised"); return MW_E_STATE; }
+    const size_t total = o->n2 * o->tiles;
+    float2* d = (float2*)htilde;
+    if (!o->device_ptrs) { int rc = ensure(&o->s_h, total); if (rc) return rc; d = o->s_h; }
+    mwk::k_evolve<<<(unsigned)((total + 255) / 256), 256, 0, o->stream>>>(o->spec, o->omega, d, (int64_t)o->n2, o->tiles, t);
+    MW_LAUNCH_CHECK();
+    if (!o->device_ptrs) {
+        MW_CUDA(cudaMemcpyAsync(htilde, d, total * sizeof(float2), cudaMemcpyDeviceToHost, o->stream));
+        MW_CUDA(cudaStreamSynchronize(o->stream));
+    }
+    return MW_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-frame launches
+// ---------------------------------------------------------------------------------------------
+template <int N, int RP>
+static int launch_rows(mw_ocean* o, const mwk::RowArgs& a)
+{
+    constexpr int threads = RP * 6 * (N / 32);
+    constexpr size_t smem = (size_t)RP * 6 * mwfft::Plan<N>::PITCH * sizeof(float2);
+    static bool attr_done[64] = {};
+    if (!attr_done[o->p.device]) {
+        MW_CUDA(cudaFuncSetAttribute(mwk::k_spectrum_rows<N, RP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done[o->p.device] = true;
+    }
+    dim3 grid(N / 2 / RP, o->tiles);
+    ProfScope ps(o, 0);
+    mwk::k_spectrum_rows<N, RP><<<grid, threads, smem, o->stream>>>(a);
+    MW_LAUNCH_CHECK();
+    return MW_OK;
+}
+
+template <int N, int W>
+static int launch_cols(mw_ocean* o, const mwk::ColArgs& a)
+{
+    constexpr int threads = (W + 1) * (N / 32);
+    constexpr size_t smem = (size_t)(W + 1) * mwfft::Plan<N>::PITCH * sizeof(float2) + (size_t)N * W * sizeof(float);
+    static bool attr_done[64] = {};
+    if (!attr_done[o->p.device]) {
+        MW_CUDA(cudaFuncSetAttribute(mwk::k_cols_extract<N, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done[o->p.device] = true;
+    }
+    dim3 grid(N / W, o->tiles);
+    ProfScope ps(o, 1);
+    mwk::k_cols_extract<N, W><<<grid, threads, smem, o->stream>>>(a);
+    MW_LAUNCH_CHECK();
+    return MW_OK;
+}
+
+static int run_frame(mw_ocean* o, const mwk::RowArgs& ra, const mwk::ColArgs& ca)
+{
+    int rc;
+    switch (o->N) {
+#define MW_CASE(N_, RP_, W_)                                         \
+    case N_:                                                         \
+        if ((rc = launch_rows<N_, RP_>(o, ra))) return rc;           \
+        return launch_cols<N_, W_>(o, ca);
+        MW_CASE(32, 16, 8)
+        MW_CASE(64, 8, 8)
+        MW_CASE(128, 4, 8)
+        MW_CASE(256, 4, 8)
+        MW_CASE(512, 2, 8)
+        case 1024:
+            if ((rc = launch_rows<1024, 1>(o, ra))) return rc;
+            return o->tiles >= 2 ? launch_cols<1024, 8>(o, ca) : launch_cols<1024, 4>(o, ca);
+        MW_CASE(2048, 1, 4)
+#undef MW_CASE
+    }
+    mw_set_error("unsupported resolution %d", o->N);
+    return MW_E_INVALID_ARG;
+}
+
+extern "C" int mw_ocean_generate(mw_ocean* o, float t, const mw_ocean_out* out)
+{
+    MW_CHECK_HANDLE(o);
+    if (!out) { mw_set_error("mw_ocean_generate: null output block"); return MW_E_INVALID_ARG; }
+    if (!o->have_h0) { mw_set_error("h0 not initialised: call mw_ocean_init_spectrum or mw_ocean_set_h0 first"); return MW_E_STATE; }
+    const size_t total = o->n2 * o->tiles;
+    const bool dev = o->device_ptrs;
+    const bool mesh = out->vertices || out->colors;
+    int rc;
+
+    // where each field is produced on the device
+    float* d_height = nullptr; float2* d_disp = nullptr; float* d_normal = nullptr; float* d_white = nullptr; float* d_jac = nullptr;
+    if (out->height || out->vertices) {
+        if (dev && out->height) d_height = out->height;
+        else { if ((rc = ensure(&o->s_height, total))) return rc; d_height = o->s_height; }
+    }
+    if (out->disp || out->vertices) {
+        if (dev && out->disp) d_disp = (float2*)out->disp;
+        else { if ((rc = ensure(&o->s_disp, total))) return rc; d_disp = o->s_disp; }
+    }
+    if (out->normal) {
+        if (dev) d_normal = out->normal;
+        else { if ((rc = ensure(&o->s_normal, total * 3))) return rc; d_normal = o->s_normal; }
+    }
+    if (out->whitecap || out->colors) {
+        if (dev && out->whitecap) d_white = out->whitecap;
+        else { if ((rc = ensure(&o->s_white, total))) return rc; d_white = o->s_white; }
+    }
+    if (out->jacobian) {
+        if (dev) d_jac = out->jacobian;
+        else { if ((rc = ensure(&o->s_jac, total))) return rc; d_jac = o->s_jac; }
+    }
+
+    mwk::RowArgs ra{o->spec, o->omega, o->ramp, o->kd, o->tw, o->X, t};
+    mwk::ColArgs ca{o->X, o->tw, d_height, d_disp, d_normal, d_white, d_jac};
+    if ((rc = run_frame(o, ra, ca))) return rc;
+
+    float* d_vert = nullptr; float4* d_col = nullptr;
+    if (mesh) {
+        if (out->vertices) {
+            if (dev) d_vert = out->vertices;
+            else { if ((rc = ensure(&o->s_vert, total * 3))) return rc; d_vert = o->s_vert; }
+        }
+        if (out->colors) {
+            if (dev) d_col = (float4*)out->colors;
+            else { if ((rc = ensure(&o->s_col, total))) return rc; d_col = o->s_col; }
+        }
+        ProfScope ps(o, 2);
+        mwk::k_mesh_outputs<<<(unsigned)((total + 255) / 256), 256, 0, o->stream>>>(
+            d_height, d_disp, d_white, d_vert, d_col, o->N, o->tiles, o->p.unit_width, o->p.choppiness);
+        MW_LAUNCH_CHECK();
+    }
+
+    if (!dev) {
+        auto d2h = [&](void* h, const void* d, size_t bytes) -> cudaError_t {
+            return h ? cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, o->stream) : cudaSuccess;
+        };
+        MW_CUDA(d2h(out->height, d_height, total * 4));
+        MW_CUDA(d2h(out->disp, d_disp, total * 8));
+        MW_CUDA(d2h(out->normal, d_normal, total * 12));
+        MW_CUDA(d2h(out->whitecap, d_white, total * 4));
+        MW_CUDA(d2h(out->jacobian, d_jac, total * 4));
+        MW_CUDA(d2h(out->vertices, d_vert, total * 12));
+        MW_CUDA(d2h(out->colors, d_col, total * 16));
+        MW_CUDA(cudaStreamSynchronize(o->stream));
+    }
+    return MW_OK;
+}
+
+extern "C" int mw_ocean_update(mw_ocean* o, float delta_time, const mw_ocean_out* out)
+{
+    if (!o) { mw_set_error("null handle"); return MW_E_INVALID_ARG; }
+    o->timer = o->timer + delta_time / o->p.t_division;  // FFTMesh.cs:70
+    return mw_ocean_generate(o, o->timer, out);          // FFTMesh.cs:72
+}
+extern "C" int mw_ocean_reset_timer(mw_ocean* o)
+{
+    if (!o) { mw_set_error("null handle"); return MW_E_INVALID_ARG; }
+    o->timer = 0.f;  // FFTMesh.cs:64
+    return MW_OK;
+}
+extern "C" float mw_ocean_timer(const mw_ocean* o) { return o ? o->timer : 0.f; }
+
+extern "C" int mw_ocean_kernel_times(mw_ocean* o, float ms[MW_KERNEL_COUNT], int64_t launches[MW_KERNEL_COUNT], int reset)
+{
+    MW_CHECK_HANDLE(o);
+    if (!o->profile) { mw_set_error("handle was not created with MW_PROFILE"); return MW_E_STATE; }
+    int rc = drain_events(o);
+    if (rc) return rc;
+    for (int k = 0; k < MW_KERNEL_COUNT; ++k) {
+        if (ms) ms[k] = (float)o->k_ms[k];
+        if (launches) launches[k] = o->k_n[k];
+        if (reset) { o->k_ms[k] = 0; o->k_n[k] = 0; }
+    }
+    return MW_OK;
+}
