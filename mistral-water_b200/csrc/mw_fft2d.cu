@@ -13,71 +13,95 @@ namespace {
 using mwfft::Plan;
 using mwfft::pad_idx;
 
-// LR lines (rows) per CTA, contiguous along the transform direction.
+// LR packed lines per CTA; packed line l holds rows 2l and 2l+1 (contiguous along the transform direction).
 template <int N, int LR, int SIGN>
-__global__ void __launch_bounds__(LR * (N / 32)) k_fft_rows(const float2* __restrict__ in, float2* __restrict__ out,
-                                                           const float2* __restrict__ tw, int rows_total)
+__global__ void __launch_bounds__(LR * (N / 16)) k_fft_rows(const float2* __restrict__ in, float2* __restrict__ out,
+                                                           const float2* __restrict__ tw, int lines_total)
 {
     using P = Plan<N>;
     constexpr int T = P::T;
+    constexpr int PITCH = mwfft::plane_pitch(N, 8);
     extern __shared__ float2 smem[];
     const int lr = threadIdx.x / T, g = threadIdx.x % T;
-    const int row = blockIdx.x * LR + lr;
-    const bool active = row < rows_total;
-    float2* line = smem + lr * P::PITCH;
+    const int line = blockIdx.x * LR + lr;
+    const bool active = line < lines_total;
+    float2* pre = smem + 2 * lr * PITCH;
+    float2* pim = pre + PITCH;
+    const float2* s0 = in + (size_t)(2 * line) * N;
+    const float2* s1 = s0 + N;
     if (active) {
-        const float2* src = in + (size_t)row * N;
 #pragma unroll
-        for (int c = 0; c < 32; ++c) line[pad_idx(g + T * c)] = src[g + T * c];
+        for (int c = 0; c < 16; ++c) {
+            const int i = g + T * c;
+            const float2 a = s0[i], b = s1[i];
+            pre[pad_idx(i)] = make_float2(a.x, b.x);
+            pim[pad_idx(i)] = make_float2(a.y, b.y);
+        }
     }
     __syncthreads();
-    float2* dst = out + (size_t)row * N;
-    mwfft::fft_line<N, SIGN>(line, g, active, tw, [&](int idx, float2 v) { dst[idx] = v; });
+    float2* d0 = out + (size_t)(2 * line) * N;
+    float2* d1 = d0 + N;
+    mwfft::fft_line<N, SIGN>(pre, pim, g, lr, active, tw, [&](int idx, mwfft::cpk v) {
+        d0[idx] = make_float2(v.re.x, v.im.x);
+        d1[idx] = make_float2(v.re.y, v.im.y);
+    });
 }
 
-// Slab of W columns per CTA: transposing load, FFT along the strided direction, transposing store.
+// Slab of W columns per CTA (W/2 packed lines): transposing load, FFT along the strided direction,
+// transposing store.
 template <int N, int W, int SIGN>
-__global__ void __launch_bounds__(W * (N / 32)) k_fft_cols(const float2* __restrict__ in, float2* __restrict__ out,
-                                                          const float2* __restrict__ tw)
+__global__ void __launch_bounds__((W / 2) * (N / 16)) k_fft_cols(const float2* __restrict__ in, float2* __restrict__ out,
+                                                                const float2* __restrict__ tw)
 {
     using P = Plan<N>;
     constexpr int T = P::T;
-    constexpr int MAIN = W * T;
+    constexpr int HL = W / 2;
+    constexpr int MAIN = HL * T;
+    constexpr int PITCH = mwfft::plane_pitch(N, HL);
     extern __shared__ float2 smem[];
     const int tid = threadIdx.x;
     const int q = tid / T, g = tid % T;
     const int b0 = blockIdx.x * W;
     const size_t base = (size_t)blockIdx.y * N * N;
 #pragma unroll
-    for (int k = 0; k < 32; ++k) {
+    for (int k = 0; k < 16; ++k) {
         const int e = tid + k * MAIN;
-        smem[(e % W) * P::PITCH + pad_idx(e / W)] = in[base + (size_t)(e / W) * N + b0 + (e % W)];
+        const int n = e / HL, c2 = e % HL;
+        const float4 v = *reinterpret_cast<const float4*>(in + base + (size_t)n * N + b0 + 2 * c2);
+        smem[2 * c2 * PITCH + pad_idx(n)] = make_float2(v.x, v.z);
+        smem[(2 * c2 + 1) * PITCH + pad_idx(n)] = make_float2(v.y, v.w);
     }
     __syncthreads();
-    float2* line = smem + q * P::PITCH;
-    mwfft::fft_line<N, SIGN>(line, g, true, tw, [&](int idx, float2 v) { line[pad_idx(idx)] = v; });
+    float2* pre = smem + 2 * q * PITCH;
+    float2* pim = pre + PITCH;
+    mwfft::fft_line<N, SIGN>(pre, pim, g, q, true, tw, [&](int idx, mwfft::cpk v) {
+        pre[pad_idx(idx)] = v.re;
+        pim[pad_idx(idx)] = v.im;
+    });
     __syncthreads();
 #pragma unroll
-    for (int k = 0; k < 32; ++k) {
+    for (int k = 0; k < 16; ++k) {
         const int e = tid + k * MAIN;
-        out[base + (size_t)(e / W) * N + b0 + (e % W)] = smem[(e % W) * P::PITCH + pad_idx(e / W)];
+        const int n = e / HL, c2 = e % HL;
+        const float2 r = smem[2 * c2 * PITCH + pad_idx(n)], i = smem[(2 * c2 + 1) * PITCH + pad_idx(n)];
+        *reinterpret_cast<float4*>(out + base + (size_t)n * N + b0 + 2 * c2) = make_float4(r.x, i.x, r.y, i.y);
     }
 }
 
 template <int N, int SIGN>
 int run2d(int batch, const float2* d_in, float2* d_tmp, float2* d_out, const float2* d_tw, cudaStream_t st)
 {
-    constexpr int T = N / 32;
-    constexpr int LR = (T >= 32) ? 4 : (128 / T);
+    constexpr int T = N / 16;
+    constexpr int LR = (T >= 64) ? 2 : (128 / T);
     constexpr int W = 8;
-    constexpr size_t smem_r = (size_t)LR * Plan<N>::PITCH * sizeof(float2);
-    constexpr size_t smem_c = (size_t)W * Plan<N>::PITCH * sizeof(float2);
+    constexpr size_t smem_r = (size_t)LR * 2 * mwfft::plane_pitch(N, 8) * sizeof(float2);
+    constexpr size_t smem_c = (size_t)(W / 2) * 2 * mwfft::plane_pitch(N, W / 2) * sizeof(float2);
     MW_CUDA(cudaFuncSetAttribute(k_fft_rows<N, LR, SIGN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r));
     MW_CUDA(cudaFuncSetAttribute(k_fft_cols<N, W, SIGN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
-    const int rows_total = batch * N;
-    k_fft_rows<N, LR, SIGN><<<(rows_total + LR - 1) / LR, LR * T, smem_r, st>>>(d_in, d_tmp, d_tw, rows_total);
+    const int lines_total = batch * N / 2;
+    k_fft_rows<N, LR, SIGN><<<(lines_total + LR - 1) / LR, LR * T, smem_r, st>>>(d_in, d_tmp, d_tw, lines_total);
     MW_LAUNCH_CHECK();
-    k_fft_cols<N, W, SIGN><<<dim3(N / W, batch), W * T, smem_c, st>>>(d_tmp, d_out, d_tw);
+    k_fft_cols<N, W, SIGN><<<dim3(N / W, batch), (W / 2) * T, smem_c, st>>>(d_tmp, d_out, d_tw);
     MW_LAUNCH_CHECK();
     return MW_OK;
 }

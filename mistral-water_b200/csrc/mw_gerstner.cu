@@ -58,13 +58,16 @@ __global__ void __launch_bounds__(THREADS) k_gerstner(const __grid_constant__ Ge
 #pragma unroll 2
     for (int w = 0; w < nw; ++w) {
         const mw_gerstner_wave W = tab.w[w];
-        const float ph = W.rate * t;  // speeds * t   (MistralWaterLib.cginc:81, :114)
-        const float ax = W.amp_xz * W.dir_x, az = W.amp_xz * W.dir_y;
+        const float ph = __fmul_rn(W.rate, t);  // speeds * t   (MistralWaterLib.cginc:81, :114)
+        const float ax = __fmul_rn(W.amp_xz, W.dir_x), az = __fmul_rn(W.amp_xz, W.dir_y);
 #pragma unroll
         for (int v = 0; v < VPT; ++v) {
-            // theta = freq * dot(dir, sVertex.xz) + rate * t   (:80-84, :114-116)
-            const float d = W.dir_x * p[3 * v + 0] + W.dir_y * p[3 * v + 2];
-            const float th = fmaf(W.freq, d, ph);
+            // theta = freq * dot(dir, sVertex.xz) + rate * t   (:80-84, :114-116).  |theta| reaches
+            // ~1e3 on a 1024-wide pond, where one fp32 ulp of theta is ~1e-4 rad: the phase is
+            // therefore formed with the source's own roundings (no FMA contraction) so that it is
+            // the same fp32 number the reference forms; only sin/cos are approximated.
+            const float d = __fadd_rn(__fmul_rn(W.dir_x, p[3 * v + 0]), __fmul_rn(W.dir_y, p[3 * v + 2]));
+            const float th = __fadd_rn(__fmul_rn(W.freq, d), ph);
             float s, c;
             sincos_reduced(th, &s, &c);
             ox[v] = fmaf(ax, c, ox[v]);       // :86 / :114
@@ -153,8 +156,9 @@ extern "C" int mw_gerstner_displace(const mw_gerstner_params* p, const float* po
     float* scratch = nullptr;
     const size_t bytes = (size_t)n * 3 * sizeof(float);
     if (!dev) {
-        MW_CUDA(cudaMalloc((void**)&scratch, bytes * (out_nrm ? 3 : 2)));
-        d_pos = scratch; d_out = scratch + 3 * n; d_nrm = out_nrm ? scratch + 6 * n : nullptr;
+        const size_t pitch = ((size_t)3 * n + 3) & ~(size_t)3;  // keep every sub-buffer 16-byte aligned (float4 I/O)
+        MW_CUDA(cudaMalloc((void**)&scratch, pitch * sizeof(float) * (out_nrm ? 3 : 2)));
+        d_pos = scratch; d_out = scratch + pitch; d_nrm = out_nrm ? scratch + 2 * pitch : nullptr;
         cudaError_t e = cudaMemcpyAsync(scratch, pos_xyz, bytes, cudaMemcpyHostToDevice, st);
         if (e != cudaSuccess) { cudaFree(scratch); mw_set_error("H2D failed: %s", cudaGetErrorString(e)); return MW_E_CUDA; }
     } else if ((reinterpret_cast<uintptr_t>(pos_xyz) | reinterpret_cast<uintptr_t>(out_xyz) |

@@ -45,7 +45,8 @@ struct mw_ocean {
     float2* ramp = nullptr;   // [2N]
     float* kd = nullptr;      // [N]
     float2* tw = nullptr;     // [N]
-    float2* X = nullptr;      // [tiles][3][N*N]
+    float4* XAB = nullptr;    // [tiles][N*N] intermediate, fields A and B (16 B / point)
+    float2* XC = nullptr;     // [tiles][N*N] intermediate, field C (8 B / point); lives right behind XAB
     // scratch outputs (host-pointer mode, or inputs of k_mesh_outputs)
     float* s_height = nullptr; float2* s_disp = nullptr; float* s_normal = nullptr; float* s_white = nullptr;
     float* s_jac = nullptr; float* s_vert = nullptr; float4* s_col = nullptr; float2* s_h = nullptr;
@@ -153,7 +154,12 @@ extern "C" int mw_ocean_create(const mw_ocean_params* params, mw_ocean** out)
     if ((rc = ensure(&o->ramp, (size_t)2 * N))) return fail(rc);
     if ((rc = ensure(&o->kd, (size_t)N))) return fail(rc);
     if ((rc = ensure(&o->tw, (size_t)N))) return fail(rc);
-    if ((rc = ensure(&o->X, o->n2 * 3 * o->tiles))) return fail(rc);
+    {
+        char* x = nullptr;  // one allocation: 24 B per grid point
+        if ((rc = ensure(&x, o->n2 * o->tiles * 24))) return fail(rc);
+        o->XAB = reinterpret_cast<float4*>(x);
+        o->XC = reinterpret_cast<float2*>(x + o->n2 * o->tiles * 16);
+    }
 
     // small host-built tables
     std::vector<float2> tw(N), ramp(2 * N);
@@ -194,7 +200,7 @@ extern "C" void mw_ocean_destroy(mw_ocean* o)
     cudaSetDevice(o->p.device);
     if (o->stream) cudaStreamSynchronize(o->stream);
     for (auto& e : o->ev_pool) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
-    void* ptrs[] = {o->spec, o->omega, o->ramp, o->kd, o->tw, o->X, o->s_height, o->s_disp, o->s_normal,
+    void* ptrs[] = {o->spec, o->omega, o->ramp, o->kd, o->tw, o->XAB, o->s_height, o->s_disp, o->s_normal,
                     o->s_white, o->s_jac, o->s_vert, o->s_col, o->s_h};
     for (void* q : ptrs) if (q) cudaFree(q);
     if (o->own_stream) cudaStreamDestroy(o->own_stream);
@@ -243,8 +249,8 @@ extern "C" int mw_ocean_set_h0(mw_ocean* o, const float* h0, const float* h0conj
     const size_t total = o->n2 * o->tiles;
     const float2 *d0 = (const float2*)h0, *d1 = (const float2*)h0conj;
     if (!o->device_ptrs) {
-        // stage through X (large enough: 3 float2 per point), then interleave on the device
-        float2* stage = o->X;
+        // stage through the intermediate buffer (24 B per point >= 2 float2), then interleave on the device
+        float2* stage = reinterpret_cast<float2*>(o->XAB);
         MW_CUDA(cudaMemcpyAsync(stage, h0, total * sizeof(float2), cudaMemcpyHostToDevice, o->stream));
         MW_CUDA(cudaMemcpyAsync(stage + total, h0conj, total * sizeof(float2), cudaMemcpyHostToDevice, o->stream));
         d0 = stage; d1 = stage + total;
@@ -263,7 +269,7 @@ extern "C" int mw_ocean_get_h0(mw_ocean* o, float* h0, float* h0conj)
     if (!o->have_h0) { mw_set_error("h0 not initialised: call mw_ocean_init_spectrum or mw_ocean_set_h0 first"); return MW_E_STATE; }
     const size_t total = o->n2 * o->tiles;
     float2 *d0 = (float2*)h0, *d1 = (float2*)h0conj;
-    if (!o->device_ptrs) { d0 = o->X; d1 = o->X + total; }
+    if (!o->device_ptrs) { d0 = reinterpret_cast<float2*>(o->XAB); d1 = d0 + total; }
     mwk::k_unpack_h0<<<(unsigned)((total + 255) / 256), 256, 0, o->stream>>>(o->spec, d0, d1, (int64_t)total);
     MW_LAUNCH_CHECK();
     if (!o->device_ptrs) {
@@ -321,36 +327,40 @@ extern "C" int mw_ocean_evolve_spectrum(mw_ocean* o, float t, float* htilde)
 // ---------------------------------------------------------------------------------------------
 // per-frame launches
 // ---------------------------------------------------------------------------------------------
-template <int N, int RP>
+template <int N, int RP, int MINB>
 static int launch_rows(mw_ocean* o, const mwk::RowArgs& a)
 {
-    constexpr int threads = RP * 6 * (N / 32);
-    constexpr size_t smem = (size_t)RP * 6 * mwfft::Plan<N>::PITCH * sizeof(float2);
+    constexpr int threads = RP * 3 * (N / 16);
+    constexpr size_t smem = (size_t)RP * 6 * mwfft::plane_pitch(N, 8) * sizeof(float2);
     static bool attr_done[64] = {};
     if (!attr_done[o->p.device]) {
-        MW_CUDA(cudaFuncSetAttribute(mwk::k_spectrum_rows<N, RP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        MW_CUDA(cudaFuncSetAttribute(mwk::k_spectrum_rows<N, RP, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        MW_CUDA(cudaFuncSetAttribute(mwk::k_spectrum_rows<N, RP, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                     cudaSharedmemCarveoutMaxShared));
         attr_done[o->p.device] = true;
     }
     dim3 grid(N / 2 / RP, o->tiles);
     ProfScope ps(o, 0);
-    mwk::k_spectrum_rows<N, RP><<<grid, threads, smem, o->stream>>>(a);
+    mwk::k_spectrum_rows<N, RP, MINB><<<grid, threads, smem, o->stream>>>(a);
     MW_LAUNCH_CHECK();
     return MW_OK;
 }
 
-template <int N, int W>
+template <int N, int W, int MINB>
 static int launch_cols(mw_ocean* o, const mwk::ColArgs& a)
 {
-    constexpr int threads = (W + 1) * (N / 32);
-    constexpr size_t smem = (size_t)(W + 1) * mwfft::Plan<N>::PITCH * sizeof(float2) + (size_t)N * W * sizeof(float);
+    constexpr int threads = (W + 1) * (N / 16);
+    constexpr size_t smem = (size_t)(W + 1) * 2 * mwfft::plane_pitch(N, W) * sizeof(float2);
     static bool attr_done[64] = {};
     if (!attr_done[o->p.device]) {
-        MW_CUDA(cudaFuncSetAttribute(mwk::k_cols_extract<N, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        MW_CUDA(cudaFuncSetAttribute(mwk::k_cols_extract<N, W, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        MW_CUDA(cudaFuncSetAttribute(mwk::k_cols_extract<N, W, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                     cudaSharedmemCarveoutMaxShared));
         attr_done[o->p.device] = true;
     }
     dim3 grid(N / W, o->tiles);
     ProfScope ps(o, 1);
-    mwk::k_cols_extract<N, W><<<grid, threads, smem, o->stream>>>(a);
+    mwk::k_cols_extract<N, W, MINB><<<grid, threads, smem, o->stream>>>(a);
     MW_LAUNCH_CHECK();
     return MW_OK;
 }
@@ -359,19 +369,17 @@ static int run_frame(mw_ocean* o, const mwk::RowArgs& ra, const mwk::ColArgs& ca
 {
     int rc;
     switch (o->N) {
-#define MW_CASE(N_, RP_, W_)                                         \
-    case N_:                                                         \
-        if ((rc = launch_rows<N_, RP_>(o, ra))) return rc;           \
-        return launch_cols<N_, W_>(o, ca);
-        MW_CASE(32, 16, 8)
-        MW_CASE(64, 8, 8)
-        MW_CASE(128, 4, 8)
-        MW_CASE(256, 4, 8)
-        MW_CASE(512, 2, 8)
-        case 1024:
-            if ((rc = launch_rows<1024, 1>(o, ra))) return rc;
-            return o->tiles >= 2 ? launch_cols<1024, 8>(o, ca) : launch_cols<1024, 4>(o, ca);
-        MW_CASE(2048, 1, 4)
+#define MW_CASE(N_, RP_, RMINB_, W_, CMINB_)                                  \
+    case N_:                                                                  \
+        if ((rc = launch_rows<N_, RP_, RMINB_>(o, ra))) return rc;            \
+        return launch_cols<N_, W_, CMINB_>(o, ca);
+        MW_CASE(32, 16, 1, 4, 1)
+        MW_CASE(64, 8, 1, 4, 1)
+        MW_CASE(128, 8, 1, 4, 1)
+        MW_CASE(256, 4, 2, 4, 2)
+        MW_CASE(512, 2, 2, 4, 2)
+        MW_CASE(1024, 1, 3, 4, 2)
+        MW_CASE(2048, 1, 1, 4, 1)
 #undef MW_CASE
     }
     mw_set_error("unsupported resolution %d", o->N);
@@ -411,8 +419,8 @@ extern "C" int mw_ocean_generate(mw_ocean* o, float t, const mw_ocean_out* out)
         else { if ((rc = ensure(&o->s_jac, total))) return rc; d_jac = o->s_jac; }
     }
 
-    mwk::RowArgs ra{o->spec, o->omega, o->ramp, o->kd, o->tw, o->X, t};
-    mwk::ColArgs ca{o->X, o->tw, d_height, d_disp, d_normal, d_white, d_jac};
+    mwk::RowArgs ra{o->spec, o->omega, o->ramp, o->kd, o->tw, o->XAB, o->XC, t};
+    mwk::ColArgs ca{o->XAB, o->XC, o->tw, d_height, d_disp, d_normal, d_white, d_jac};
     if ((rc = run_frame(o, ra, ca))) return rc;
 
     float* d_vert = nullptr; float4* d_col = nullptr;

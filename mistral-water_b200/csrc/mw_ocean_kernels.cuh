@@ -3,7 +3,7 @@
 // Frame pipeline (replaces FFTMesh.EvaluateWaves, Scripts/FFTMesh.cs:224-280):
 //
 //   k_spectrum_rows   h0,h0conj --evolve--> h(k,t) --phase ramp + Hermitian packing--> 3 complex
-//                     fields --row FFT (along m)--> intermediate X[f][n][b]          (pass 1)
+//                     fields --row FFT (along m)--> intermediate XAB / XC            (pass 1)
 //   k_cols_extract    X --column FFT (along n)--> height / hds / normal / whitecap   (pass 2)
 //
 // Why this equals the reference's O(N^4) direct sum: SURVEY.md section 3.4 / DESIGN.md.
@@ -139,91 +139,124 @@ __global__ void k_evolve(const float4* __restrict__ spec, const float* __restric
 // =============================================================================================
 // pass 1: evolve + pack + row FFT
 // =============================================================================================
+// Intermediate layout (ours to choose; 24 B per grid point):
+//   XAB[tile][n][b] : float4 (A.re, B.re, A.im, B.im)   A = chop-displacement field, B = slope field
+//   XC [tile][n][b] : float2 (C.re, C.im)               C = height field
 struct RowArgs {
     const float4* spec;    // [tiles][N][N]  (h0, h0conj)
     const float* omega;    // [N][N]
     const float2* ramp;    // [2N]  exp(i pi s (1-N)/N), s = n + m
     const float* kd;       // [N]   2 pi (i - N/2) / L, fp32 as FFTMesh.cs:201
     const float2* tw;      // [N]   exp(+2 pi i x / N)
-    float2* X;             // [tiles][3][N][N]
+    float4* XAB;           // [tiles][N][N]
+    float2* XC;            // [tiles][N][N]
     float t;
 };
 
-// RP row pairs per CTA; 6 lines per pair (2 rows x 3 fields); N/32 threads per line.
-template <int N, int RP>
-__global__ void __launch_bounds__(RP * 6 * (N / 32)) k_spectrum_rows(const RowArgs a)
+// F[n,m] = (p1 * e1 - p2 * conj(e2)) * (-i/2): the Hermitian "imaginary part" packing of SURVEY 3.4
+__device__ __forceinline__ float2 herm_pack(float2 p1, float2 e1, float2 p2, float2 e2)
+{
+    const float2 d = csub(cmul(p1, e1), cmul(p2, cconj(e2)));
+    return make_float2(0.5f * d.y, -0.5f * d.x);
+}
+
+// RP row pairs per CTA; 3 packed lines per pair: (A,B) of row rA, (A,B) of row rB, (C of rA, C of rB).
+template <int N, int RP, int MINB>
+__global__ void __launch_bounds__(RP * 3 * (N / 16), MINB) k_spectrum_rows(const RowArgs a)
 {
     using P = Plan<N>;
     constexpr int T = P::T;
-    constexpr int PAIR_THREADS = 6 * T;
+    constexpr int PAIR_THREADS = 3 * T;
+    constexpr int PITCH = mwfft::plane_pitch(N, 8);
     extern __shared__ float2 smem[];
 
     const int tile = blockIdx.y;
     const int rp = threadIdx.x / PAIR_THREADS;
     const int lt = threadIdx.x % PAIR_THREADS;
     const int pair = blockIdx.x * RP + rp;  // < N/2
-    float2* lines = smem + rp * 6 * P::PITCH;
+    float2* lines = smem + rp * 6 * PITCH;  // line q: re plane at (2q) * PITCH, im plane at (2q+1) * PITCH
 
-    const int rA = pair == 0 ? 0 : pair;
-    const int rB = pair == 0 ? N / 2 : N - pair;
+    const bool special = pair == 0;         // rows 0 and N/2 mirror onto themselves
+    const int rA = special ? 0 : pair;
+    const int rB = special ? N / 2 : N - pair;
     const float4* spec = a.spec + (size_t)tile * N * N;
+    const float kxA = __ldg(a.kd + rA), kxB = __ldg(a.kd + rB);
 
-    // ---- evolve + pack: one task = a grid point and its mirror (-k) ----
-    const int ntask = pair == 0 ? N + 2 : N;
-    for (int task = lt; task < ntask; task += PAIR_THREADS) {
-        int n1, m1, n2, m2, sel1, sel2;
-        if (pair != 0) {
-            n1 = rA; m1 = task; n2 = rB; m2 = (N - task) & (N - 1); sel1 = 0; sel2 = 1;
-        } else {  // rows 0 and N/2 mirror onto themselves
-            const int half = task >= N / 2 + 1;
-            n1 = n2 = half ? N / 2 : 0;
-            m1 = task - half * (N / 2 + 1);
-            m2 = (N - m1) & (N - 1);
-            sel1 = sel2 = half;
+    // ---- evolve + pack.  One task = the four grid points (rA|rB, m|m') with m' = -m mod N; the set is
+    //      closed under k -> -k, so every Hermitian partner is on hand and every point is read once. ----
+    for (int m = lt; m <= N / 2; m += PAIR_THREADS) {
+        const int mm = (N - m) & (N - 1);
+        const float4 s1 = ldg_stream4(spec + rA * N + m);    // P1 = (rA, m)
+        const float4 s2 = ldg_stream4(spec + rB * N + mm);   // P2 = (rB, m')
+        const float4 s3 = ldg_stream4(spec + rA * N + mm);   // P3 = (rA, m')
+        const float4 s4 = ldg_stream4(spec + rB * N + m);    // P4 = (rB, m)
+        // omega depends on |k| only: general rows  w(P1) = w(P2), w(P3) = w(P4);
+        //                            special rows  w(P1) = w(P3), w(P4) = w(P2)
+        const float w1 = __ldg(a.omega + rA * N + m);
+        const float w2 = __ldg(a.omega + (special ? rB * N + m : rA * N + mm));
+        float sn1, cs1, sn2, cs2;
+        sincosf(__fmul_rn(w1, a.t), &sn1, &cs1);  // FFTMesh.cs:183
+        sincosf(__fmul_rn(w2, a.t), &sn2, &cs2);
+        const float2 E1 = cmul(htilde_eval(s1, cs1, sn1), __ldg(a.ramp + rA + m));
+        const float2 E2 = cmul(special ? htilde_eval(s2, cs2, sn2) : htilde_eval(s2, cs1, sn1), __ldg(a.ramp + rB + mm));
+        const float2 E3 = cmul(special ? htilde_eval(s3, cs1, sn1) : htilde_eval(s3, cs2, sn2), __ldg(a.ramp + rA + mm));
+        const float2 E4 = cmul(htilde_eval(s4, cs2, sn2), __ldg(a.ramp + rB + m));
+        const float kzm = __ldg(a.kd + m), kzmm = __ldg(a.kd + mm);
+        // |k| is shared inside a mirror pair; it differs between rows A and B only for the special pair
+        const float k2A = kxA * kxA + kzm * kzm, k2B = kxB * kxB + kzm * kzm;
+        const float invA = k2A < MW_EPSILON_F * MW_EPSILON_F ? 0.0f : rsqrtf(k2A);  // FFTMesh.cs:213-214
+        const float invB = k2B < MW_EPSILON_F * MW_EPSILON_F ? 0.0f : rsqrtf(k2B);
+        const float2 k1 = make_float2(kxA, kzm), k2 = make_float2(kxB, kzmm), k3 = make_float2(kxA, kzmm), k4 = make_float2(kxB, kzm);
+        const float2 u1 = make_float2(k1.x * invA, k1.y * invA), u3 = make_float2(k3.x * invA, k3.y * invA);
+        const float2 u2 = make_float2(k2.x * invB, k2.y * invB), u4 = make_float2(k4.x * invB, k4.y * invB);
+        float2 A1, A2, A3, A4, B1, B2, B3, B4;
+        if (!special) {  // partners: P1 <-> P2, P3 <-> P4
+            A1 = herm_pack(u1, E1, u2, E2); A2 = herm_pack(u2, E2, u1, E1);
+            A3 = herm_pack(u3, E3, u4, E4); A4 = herm_pack(u4, E4, u3, E3);
+            B1 = herm_pack(k1, E1, k2, E2); B2 = herm_pack(k2, E2, k1, E1);
+            B3 = herm_pack(k3, E3, k4, E4); B4 = herm_pack(k4, E4, k3, E3);
+        } else {         // partners: P1 <-> P3, P4 <-> P2
+            A1 = herm_pack(u1, E1, u3, E3); A3 = herm_pack(u3, E3, u1, E1);
+            A4 = herm_pack(u4, E4, u2, E2); A2 = herm_pack(u2, E2, u4, E4);
+            B1 = herm_pack(k1, E1, k3, E3); B3 = herm_pack(k3, E3, k1, E1);
+            B4 = herm_pack(k4, E4, k2, E2); B2 = herm_pack(k2, E2, k4, E4);
         }
-        const float4 s1 = ldg_stream4(spec + n1 * N + m1);
-        const float4 s2 = ldg_stream4(spec + n2 * N + m2);
-        const float omegat = __fmul_rn(__ldg(a.omega + n1 * N + m1), a.t);  // FFTMesh.cs:183
-        float sn, cs;
-        sincosf(omegat, &sn, &cs);
-        const float2 E1 = cmul(htilde_eval(s1, cs, sn), __ldg(a.ramp + n1 + m1));
-        const float2 E2 = cmul(htilde_eval(s2, cs, sn), __ldg(a.ramp + n2 + m2));
-        const float kx1 = __ldg(a.kd + n1), kz1 = __ldg(a.kd + m1);
-        const float kx2 = __ldg(a.kd + n2), kz2 = __ldg(a.kd + m2);
-        const float k2 = kx1 * kx1 + kz1 * kz1;
-        const float inv = k2 < MW_EPSILON_F * MW_EPSILON_F ? 0.0f : rsqrtf(k2);  // FFTMesh.cs:213-214
-        const float2 E1c = cconj(E1), E2c = cconj(E2);
-        // F[n,m] = ((p1) E1 - (p2) conj(E2)) * (-i/2), p = (kx + i kz) or (kx + i kz)/|k|
-        auto pack = [](float2 p1, float2 e1, float2 p2, float2 e2c) {
-            const float2 d = csub(cmul(p1, e1), cmul(p2, e2c));
-            return make_float2(0.5f * d.y, -0.5f * d.x);
-        };
-        const float2 pk1 = make_float2(kx1, kz1), pk2 = make_float2(kx2, kz2);
-        const float2 pu1 = make_float2(kx1 * inv, kz1 * inv), pu2 = make_float2(kx2 * inv, kz2 * inv);
-        float2* l1 = lines + sel1 * 3 * P::PITCH + pad_idx(m1);
-        float2* l2 = lines + sel2 * 3 * P::PITCH + pad_idx(m2);
-        l1[0] = pack(pu1, E1, pu2, E2c);            // field 0: chop displacement (Dx, Dz)
-        l1[P::PITCH] = pack(pk1, E1, pk2, E2c);     // field 1: slopes (sx, sz)
-        l1[2 * P::PITCH] = E1;                      // field 2: height
-        l2[0] = pack(pu2, E2, pu1, E1c);
-        l2[P::PITCH] = pack(pk2, E2, pk1, E1c);
-        l2[2 * P::PITCH] = E2;
+        const int pm = pad_idx(m), pmm = pad_idx(mm);
+        // line 0 = (A,B) of row rA ; line 1 = (A,B) of row rB ; line 2 = (C of rA, C of rB)
+        lines[0 * PITCH + pm] = make_float2(A1.x, B1.x);  lines[1 * PITCH + pm] = make_float2(A1.y, B1.y);
+        lines[0 * PITCH + pmm] = make_float2(A3.x, B3.x); lines[1 * PITCH + pmm] = make_float2(A3.y, B3.y);
+        lines[2 * PITCH + pm] = make_float2(A4.x, B4.x);  lines[3 * PITCH + pm] = make_float2(A4.y, B4.y);
+        lines[2 * PITCH + pmm] = make_float2(A2.x, B2.x); lines[3 * PITCH + pmm] = make_float2(A2.y, B2.y);
+        lines[4 * PITCH + pm] = make_float2(E1.x, E4.x);  lines[5 * PITCH + pm] = make_float2(E1.y, E4.y);
+        lines[4 * PITCH + pmm] = make_float2(E3.x, E2.x); lines[5 * PITCH + pmm] = make_float2(E3.y, E2.y);
     }
     __syncthreads();
 
-    // ---- row FFT: line q = sel * 3 + field ----
+    // ---- row FFT of the three packed lines ----
     const int q = lt / T, g = lt % T;
-    const int sel = q / 3, f = q % 3;
-    const int row = sel ? rB : rA;
-    float2* dst = a.X + (((size_t)tile * 3 + f) * N + row) * N;
-    mwfft::fft_line<N, +1>(lines + q * P::PITCH, g, true, a.tw, [&](int idx, float2 v) { dst[idx] = v; });
+    float2* pre = lines + 2 * q * PITCH;
+    float2* pim = pre + PITCH;
+    const size_t tbase = (size_t)tile * N * N;
+    if (q < 2) {
+        float4* dst = a.XAB + tbase + (size_t)(q ? rB : rA) * N;
+        mwfft::fft_line<N, +1>(pre, pim, g, rp * 3 + q, true, a.tw,
+                               [&](int idx, mwfft::cpk v) { dst[idx] = make_float4(v.re.x, v.re.y, v.im.x, v.im.y); });
+    } else {
+        float2* dA = a.XC + tbase + (size_t)rA * N;
+        float2* dB = a.XC + tbase + (size_t)rB * N;
+        mwfft::fft_line<N, +1>(pre, pim, g, rp * 3 + q, true, a.tw, [&](int idx, mwfft::cpk v) {
+            dA[idx] = make_float2(v.re.x, v.im.x);
+            dB[idx] = make_float2(v.re.y, v.im.y);
+        });
+    }
 }
 
 // =============================================================================================
 // pass 2: column FFT + extraction (+ Jacobian whitecap)
 // =============================================================================================
 struct ColArgs {
-    const float2* X;    // [tiles][3][N][N]
+    const float4* XAB;  // [tiles][N][N]
+    const float2* XC;   // [tiles][N][N]
     const float2* tw;   // [N]
     float* height;      // [tiles][N*N]     or NULL
     float2* disp;       // [tiles][N*N]     or NULL   (hds)
@@ -232,114 +265,157 @@ struct ColArgs {
     float* jacobian;    // [tiles][N*N]     or NULL
 };
 
-// Slab of W columns per CTA; W + 1 thread groups (the last one transforms the halo column b0 + W of
-// the displacement field so that hds[index + 1] of FFTMesh.cs:266 is on chip).
-template <int N, int W>
-__global__ void __launch_bounds__((W + 1) * (N / 32)) k_cols_extract(const ColArgs a)
+// Slab of W columns per CTA, W + 1 packed-line thread groups.
+//   phase 1: the (A,B) pairs of the W columns + the halo column b0 + W (so that hds[index + 1] of
+//            FFTMesh.cs:266 is on chip)  -> hds, normal, Jacobian, whitecap
+//   phase 2: the C field of the W columns, two columns per packed line  -> height
+template <int N, int W, int MINB>
+__global__ void __launch_bounds__((W + 1) * (N / 16), MINB) k_cols_extract(const ColArgs a)
 {
     using P = Plan<N>;
     constexpr int T = P::T;
     constexpr int MAIN = W * T;  // threads that own the W real columns
-    extern __shared__ float2 smem[];
-    float2* lines = smem;                                               // [W + 1][PITCH]
-    float* noise = reinterpret_cast<float*>(smem + (W + 1) * P::PITCH); // [N][W]
+    constexpr int PITCH = mwfft::plane_pitch(N, W);
+    constexpr int LOGW = mwfft::ilog2(W);
+    extern __shared__ float2 smem[];  // line q: re plane at (2q) * PITCH, im plane at (2q+1) * PITCH
 
     const int tile = blockIdx.y;
     const int b0 = blockIdx.x * W;
     const int tid = threadIdx.x;
     const int q = tid / T, g = tid % T;
     const bool is_halo = q == W;
-    const bool halo_live = b0 + W < N;
     const size_t plane = (size_t)N * N;
     const size_t obase = (size_t)tile * plane;
     const bool want_white = a.whitecap != nullptr || a.jacobian != nullptr;
+    const bool halo_live = want_white && b0 + W < N;
 
-    // field order: 2 (height), 1 (slopes -> normal, noise), 0 (displacement -> hds, Jacobian)
-#pragma unroll 1
-    for (int f = 2; f >= 0; --f) {
-        const float2* Xf = a.X + ((size_t)tile * 3 + f) * plane;
-        const bool skip = (f == 2 && !a.height) || (f == 1 && !a.normal && !want_white) ||
-                          (f == 0 && !a.disp && !want_white);
-        if (skip) continue;  // uniform across the CTA
-        // ---- transposing load: rows of W float2 from global -> line c at position n ----
+    // ------------------------------------------------------------------ phase 1: (A, B)
+    if (a.disp || a.normal || want_white) {
+        const float4* X = a.XAB + obase;
         if (!is_halo) {
-            float2 v[32];
+            float4 v[16];
 #pragma unroll
-            for (int k = 0; k < 32; ++k) {
+            for (int k = 0; k < 16; ++k) {
                 const int e = tid + k * MAIN;
-                v[k] = __ldg(Xf + (size_t)(e / W) * N + b0 + (e % W));
+                v[k] = __ldg(X + (size_t)(e >> LOGW) * N + b0 + (e & (W - 1)));
             }
 #pragma unroll
-            for (int k = 0; k < 32; ++k) {
+            for (int k = 0; k < 16; ++k) {
                 const int e = tid + k * MAIN;
-                lines[(e % W) * P::PITCH + pad_idx(e / W)] = v[k];
+                const int o = 2 * (e & (W - 1)) * PITCH + pad_idx(e >> LOGW);
+                smem[o] = make_float2(v[k].x, v[k].y);
+                smem[o + PITCH] = make_float2(v[k].z, v[k].w);
             }
-        } else if (f == 0 && halo_live && want_white) {
+        } else if (halo_live) {
 #pragma unroll
-            for (int k = 0; k < 32; ++k) {
+            for (int k = 0; k < 16; ++k) {
                 const int n = g + k * T;
-                lines[W * P::PITCH + pad_idx(n)] = __ldg(Xf + (size_t)n * N + b0 + W);
+                const float4 h = __ldg(X + (size_t)n * N + b0 + W);
+                smem[2 * W * PITCH + pad_idx(n)] = make_float2(h.x, h.y);
+                smem[(2 * W + 1) * PITCH + pad_idx(n)] = make_float2(h.z, h.w);
             }
         }
         __syncthreads();
-        // ---- column FFT; results (sign-fixed, real pairs) go back into the line ----
         {
-            const bool active = !is_halo || (f == 0 && halo_live && want_white);
-            float2* line = lines + q * P::PITCH;
+            float2* pre = smem + 2 * q * PITCH;
+            float2* pim = pre + PITCH;
             const int b = b0 + q;
-            // sigma[a,b] = -(-1)^(a+b); displacement field also carries Dz's extra minus (FFTMesh.cs:215)
-            mwfft::fft_line<N, +1>(line, g, active, a.tw, [&](int idx, float2 v) {
+            // sigma[a,b] = -(-1)^(a+b); lane x = field A -> (dx, dz) with Dz's extra minus (FFTMesh.cs:215),
+            // lane y = field B -> (sx, sz).  Stored back as re plane = (dx, sx), im plane = (dz, sz).
+            mwfft::fft_line<N, +1>(pre, pim, g, q, !is_halo || halo_live, a.tw, [&](int idx, mwfft::cpk v) {
                 const float s = ((idx + b) & 1) ? 1.0f : -1.0f;
-                line[pad_idx(idx)] = make_float2(s * v.x, f == 0 ? -s * v.y : s * v.y);
+                const int p = pad_idx(idx);
+                pre[p] = make_float2(s * v.re.x, s * v.re.y);
+                pim[p] = make_float2(-s * v.im.x, s * v.im.y);
             });
         }
         __syncthreads();
-        // ---- extraction: thread <-> (row a = e / W, column c = e % W), c fastest ----
         if (!is_halo) {
 #pragma unroll 4
-            for (int k = 0; k < 32; ++k) {
+            for (int k = 0; k < 16; ++k) {
                 const int e = tid + k * MAIN;
-                const int ar = e / W, c = e % W;
+                const int ar = e >> LOGW, c = e & (W - 1);
                 const size_t o = obase + (size_t)ar * N + b0 + c;
-                const float2 val = lines[c * P::PITCH + pad_idx(ar)];
-                if (f == 2) {
-                    a.height[o] = val.x;  // FFTMesh.cs:219 h.x
-                } else if (f == 1) {
-                    // nor = normalize(up - n) = (sx, 1, sz) / |.|   (FFTMesh.cs:212, 218)
-                    const float inv = rsqrtf(val.x * val.x + 1.0f + val.y * val.y);
-                    const float nx = val.x * inv, ny = inv, nz = val.y * inv;
-                    if (a.normal) {
-                        a.normal[3 * o + 0] = nx;
-                        a.normal[3 * o + 1] = ny;
-                        a.normal[3 * o + 2] = nz;
+                const float2* pre = smem + 2 * c * PITCH;
+                const float2* pim = pre + PITCH;
+                const float2 vr = pre[pad_idx(ar)], vi = pim[pad_idx(ar)];  // (dx, sx), (dz, sz)
+                // nor = normalize(up - n) = (sx, 1, sz) / |.|   (FFTMesh.cs:212, 218)
+                const float inv = rsqrtf(vr.y * vr.y + 1.0f + vi.y * vi.y);
+                const float nx = vr.y * inv, nz = vi.y * inv;
+                if (a.normal) {
+                    a.normal[3 * o + 0] = nx;
+                    a.normal[3 * o + 1] = inv;
+                    a.normal[3 * o + 2] = nz;
+                }
+                if (a.disp) a.disp[o] = make_float2(vr.x, vi.x);  // hds (FFTMesh.cs:247)
+                if (want_white) {
+                    float2 dDdx = make_float2(0.f, 0.f), dDdy = make_float2(0.f, 0.f);
+                    if (ar != N - 1) {  // hds[index + resolution]  (:260-263)
+                        const float nbx = pre[pad_idx(ar + 1)].x, nbz = pim[pad_idx(ar + 1)].x;
+                        dDdx = make_float2(0.5f * (vr.x - nbx), 0.5f * (vi.x - nbz));
                     }
-                    // noise = |(|n.x|, |n.z|) * 0.3|   (FFTMesh.cs:269-270)
-                    const float ax = fabsf(nx) * 0.3f, az = fabsf(nz) * 0.3f;
-                    noise[ar * W + c] = sqrtf(ax * ax + az * az);
-                } else {
-                    if (a.disp) a.disp[o] = val;  // hds (FFTMesh.cs:247)
-                    if (want_white) {
-                        float2 dDdx = make_float2(0.f, 0.f), dDdy = make_float2(0.f, 0.f);
-                        if (ar != N - 1) {  // hds[index + resolution]  (:260-263)
-                            const float2 nb = lines[c * P::PITCH + pad_idx(ar + 1)];
-                            dDdx = make_float2(0.5f * (val.x - nb.x), 0.5f * (val.y - nb.y));
-                        }
-                        if (b0 + c != N - 1) {  // hds[index + 1]  (:264-267)
-                            const float2 nb = lines[(c + 1) * P::PITCH + pad_idx(ar)];
-                            dDdy = make_float2(0.5f * (val.x - nb.x), 0.5f * (val.y - nb.y));
-                        }
-                        const float jac = (1.0f + dDdx.x) * (1.0f + dDdy.y) - dDdx.y * dDdy.x;  // :268
-                        if (a.jacobian) a.jacobian[o] = jac;
-                        if (a.whitecap) {
-                            float turb = fmaxf(1.0f - jac + noise[ar * W + c], 0.0f);  // :270
-                            turb = fminf(turb, 1.0f);                                  // SmoothStep clamps
-                            a.whitecap[o] = -2.0f * turb * turb * turb + 3.0f * turb * turb;  // :273
-                        }
+                    if (b0 + c != N - 1) {  // hds[index + 1]  (:264-267)
+                        const float nbx = pre[2 * PITCH + pad_idx(ar)].x, nbz = pim[2 * PITCH + pad_idx(ar)].x;
+                        dDdy = make_float2(0.5f * (vr.x - nbx), 0.5f * (vi.x - nbz));
+                    }
+                    const float jac = (1.0f + dDdx.x) * (1.0f + dDdy.y) - dDdx.y * dDdy.x;  // :268
+                    if (a.jacobian) a.jacobian[o] = jac;
+                    if (a.whitecap) {
+                        // noise = |(|n.x|, |n.z|) * 0.3|   (:269-270)
+                        const float ax = fabsf(nx) * 0.3f, az = fabsf(nz) * 0.3f;
+                        float turb = fmaxf(1.0f - jac + sqrtf(ax * ax + az * az), 0.0f);  // :270
+                        turb = fminf(turb, 1.0f);                                          // SmoothStep clamps
+                        a.whitecap[o] = -2.0f * turb * turb * turb + 3.0f * turb * turb;   // :273
                     }
                 }
             }
         }
         __syncthreads();
+    }
+
+    // ------------------------------------------------------------------ phase 2: C (height), W/2 packed lines
+    if (a.height) {
+        constexpr int HL = W / 2;       // packed lines
+        constexpr int HMAIN = HL * T;   // threads at work
+        const float2* X = a.XC + obase;
+        const bool on = tid < HMAIN;
+        if (on) {
+            float4 v[16];  // (C[n][b].re, C[n][b].im, C[n][b+1].re, C[n][b+1].im)
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                const int e = tid + k * HMAIN;
+                const int n = e / HL, c2 = e % HL;
+                v[k] = __ldg(reinterpret_cast<const float4*>(X + (size_t)n * N + b0 + 2 * c2));
+            }
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                const int e = tid + k * HMAIN;
+                const int n = e / HL, c2 = e % HL;
+                const int o = 2 * c2 * PITCH + pad_idx(n);
+                smem[o] = make_float2(v[k].x, v[k].z);
+                smem[o + PITCH] = make_float2(v[k].y, v[k].w);
+            }
+        }
+        __syncthreads();
+        {
+            float2* pre = smem + 2 * q * PITCH;
+            float2* pim = pre + PITCH;
+            const int b = b0 + 2 * q;  // lane x = column b, lane y = column b + 1 (opposite sigma)
+            mwfft::fft_line<N, +1>(pre, pim, g, q, on, a.tw, [&](int idx, mwfft::cpk v) {
+                const float s = ((idx + b) & 1) ? 1.0f : -1.0f;
+                pre[pad_idx(idx)] = make_float2(s * v.re.x, -s * v.re.y);  // height = sigma * Re (FFTMesh.cs:219)
+            });
+        }
+        __syncthreads();
+        if (on) {
+#pragma unroll 4
+            for (int k = 0; k < 16; ++k) {
+                const int e = tid + k * HMAIN;
+                const int n = e / HL, c2 = e % HL;
+                const float2 h = smem[2 * c2 * PITCH + pad_idx(n)];
+                *reinterpret_cast<float2*>(a.height + obase + (size_t)n * N + b0 + 2 * c2) = h;
+            }
+        }
     }
 }
 

@@ -1,0 +1,142 @@
+"""Independent ocean tiles sharded one-per-GPU, with ONE all-gather of the final float buffers
+(BASELINE config 5).
+
+One process per GPU (torchrun); rank r owns tiles [r * tpr, (r + 1) * tpr).  Tiles never exchange
+data while being generated (nothing in FFTMesh.cs couples two meshes), so the only collective is
+the final in-place all-gather: every rank's engine writes its outputs straight into its own slot of
+the gather buffer (device pointers handed to mw_ocean_generate), then
+`all_gather_into_tensor(gather, gather[rank])` runs over NCCL / NVLink.
+
+torch is used for what it is good at here -- device memory, streams, the process group.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+
+FIELDS = (("height", 1), ("disp", 2), ("normal", 3), ("whitecap", 1))  # 7 floats = 28 B per grid point
+FLOATS_PER_POINT = sum(c for _, c in FIELDS)
+
+
+@dataclass(frozen=True)
+class TileLayout:
+    """Where each field of each rank lives inside the gather buffer [world][slot_floats]."""
+    N: int
+    world: int
+    tiles_per_rank: int = 1
+
+    @property
+    def points_per_rank(self) -> int:
+        return self.tiles_per_rank * self.N * self.N
+
+    @property
+    def slot_floats(self) -> int:
+        return self.points_per_rank * FLOATS_PER_POINT
+
+    @property
+    def slot_bytes(self) -> int:
+        return self.slot_floats * 4
+
+    def field_range(self, name: str) -> tuple[int, int]:
+        """[begin, end) float offsets of a field inside one slot: fields are planar, [tile][idx][comp]."""
+        off = 0
+        for f, c in FIELDS:
+            n = self.points_per_rank * c
+            if f == name:
+                return off, off + n
+            off += n
+        raise KeyError(name)
+
+    def global_tile(self, rank: int, local: int) -> int:
+        return rank * self.tiles_per_rank + local
+
+    def owner(self, global_tile: int) -> tuple[int, int]:
+        return divmod(global_tile, self.tiles_per_rank)
+
+
+def tile_wind(base_wind, global_tile: int, step_deg: float = 45.0):
+    """Config 5: tile k's wind is the base wind rotated by 45 deg * k."""
+    a = math.radians(step_deg * global_tile)
+    c, s = math.cos(a), math.sin(a)
+    return (c * base_wind[0] - s * base_wind[1], s * base_wind[0] + c * base_wind[1])
+
+
+class ShardedTiles:
+    """This rank's share of the tile set + the gather buffer.
+
+    `make_generator(rank_params) -> callable(t, slot_views: dict[str, Tensor])` builds the local
+    producer; the default is the CUDA engine (mistral_water_b200.Ocean with device pointers).  The
+    CPU `gloo` tests inject a stub there to exercise the sharding / layout / collective logic.
+    """
+
+    def __init__(self, N: int, rank: int, world: int, tiles_per_rank: int = 1, base_seed: int = 1000,
+                 wind=(5.0, 3.0), amplitude: float = 0.01, unit_width: float = 1.0, choppiness: float = 1.0,
+                 device=None, group=None, make_generator=None):
+        import torch
+
+        self.torch = torch
+        self.layout = TileLayout(N, world, tiles_per_rank)
+        self.rank, self.world, self.group = rank, world, group
+        self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.gather = torch.empty((world, self.layout.slot_floats), dtype=torch.float32, device=self.device)
+        self.rank_params = dict(resolution=N, unit_width=unit_width, choppiness=choppiness, amplitude=amplitude,
+                                wind=tile_wind(wind, self.layout.global_tile(rank, 0)),
+                                seed=base_seed + self.layout.global_tile(rank, 0), tiles=tiles_per_rank)
+        self._gen = (make_generator or self._cuda_generator)(self.rank_params)
+
+    def _cuda_generator(self, rp):
+        from .ocean import Ocean
+
+        torch = self.torch
+        dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.stream = torch.cuda.Stream(device=self.device)
+        self.ocean = Ocean(device=dev_index, device_ptrs=True, **rp)
+        self.ocean.set_stream(self.stream.cuda_stream)
+        self.ocean.init_spectrum()
+        self.ocean.sync()
+
+        def run(t, views):
+            self.ocean.generate(t, views)
+
+        return run
+
+    def slot_views(self, rank: int | None = None) -> dict:
+        """Field views into one rank's slot (default: ours)."""
+        slot = self.gather[self.rank if rank is None else rank]
+        out = {}
+        for name, comps in FIELDS:
+            b, e = self.layout.field_range(name)
+            out[name] = slot[b:e]
+        return out
+
+    def generate_local(self, t: float) -> None:
+        """Produce this rank's tiles into its slot (asynchronous on the engine's stream)."""
+        self._gen(float(t), self.slot_views())
+
+    def all_gather(self) -> None:
+        """The one collective: in-place all-gather of the slots."""
+        import torch.distributed as dist
+
+        if self.world == 1:
+            return
+        dist.all_gather_into_tensor(self.gather.view(-1), self.gather[self.rank].view(-1), group=self.group)
+
+    def generate(self, t: float):
+        torch = self.torch
+        self.generate_local(t)
+        if hasattr(self, "stream"):
+            torch.cuda.current_stream(self.device).wait_stream(self.stream)  # NCCL runs after the producer
+        self.all_gather()
+        return self.gather
+
+    def tile_view(self, global_tile: int, name: str):
+        """Field `name` of any tile, from the gathered buffer: [N*N, comps]."""
+        r, l = self.layout.owner(global_tile)
+        b, e = self.layout.field_range(name)
+        comps = dict(FIELDS)[name]
+        n2 = self.layout.N * self.layout.N
+        return self.gather[r, b:e].view(self.layout.tiles_per_rank, n2, comps)[l]
+
+    def close(self) -> None:
+        if hasattr(self, "ocean"):
+            self.ocean.close()

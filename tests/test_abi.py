@@ -1,0 +1,97 @@
+"""CPU tests of the drop-in boundary: the shared library loads without a GPU, exports every symbol
+include/mistral_ocean.h declares, its structs have the layout the header states, and it fails loudly
+(status code + message, no crash, no fallback) when there is no device."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header():
+    return open(os.path.join(ROOT, "include", "mistral_ocean.h")).read()
+
+
+def test_library_exports_every_declared_symbol(mw):
+    declared = set(re.findall(r"\b(mw_[a-z0-9_]+)\s*\(", _header()))
+    assert declared, "header parse failed"
+    lib = mw.native.load()
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/mistral_ocean.h but not exported"
+    assert declared == set(mw.native.EXPORTS)
+
+
+def test_version_and_error_text(mw):
+    lib = mw.native.load()
+    assert lib.mw_version() == int(re.search(r"#define MW_VERSION (\d+)", _header()).group(1))
+    assert isinstance(lib.mw_last_error(), bytes)
+
+
+def test_struct_layouts_match_header(mw):
+    n = mw.native
+    assert C.sizeof(n.OceanParams) == 56 and n.OceanParams.seed.offset == 32
+    assert C.sizeof(n.OceanOut) == 7 * 8
+    assert C.sizeof(n.GerstnerWave) == 24
+    assert C.sizeof(n.GerstnerParams) == 16 + 64 * 24
+    fields = re.search(r"typedef struct mw_ocean_params \{(.*?)\} mw_ocean_params;", _header(), re.S).group(1)
+    names = re.findall(r"\b(?:int32_t|uint32_t|uint64_t|float)\s+([a-z_0-9]+);", fields)
+    assert names == [f[0] for f in n.OceanParams._fields_]
+    out_fields = re.search(r"typedef struct mw_ocean_out \{(.*?)\} mw_ocean_out;", _header(), re.S).group(1)
+    assert re.findall(r"float\*\s+([a-z]+);", out_fields) == [f[0] for f in n.OceanOut._fields_]
+
+
+@pytest.mark.parametrize("kw,frag", [
+    (dict(resolution=100), "power of two"),            # FFT Mesh scene's N=12-style grids: rejected, no O(N^4) path
+    (dict(resolution=16), "power of two"),
+    (dict(resolution=4096), "power of two"),
+    (dict(resolution=64, length=12.39), "periodic"),   # length != resolution * unit_width
+    (dict(resolution=64, unit_width=-1.0, length=-64.0), "positive"),
+    (dict(resolution=64, tiles=0), "tiles"),
+    (dict(resolution=64, t_division=0.0), "t_division"),
+])
+def test_create_validates_before_touching_the_gpu(mw, kw, frag):
+    with pytest.raises(mw.native.MwError) as ei:
+        mw.Ocean(**kw)
+    assert ei.value.code == mw.native.MW_E_INVALID_ARG
+    assert frag in ei.value.message
+
+
+def test_null_arguments_are_errors_not_crashes(mw):
+    lib = mw.native.load()
+    assert lib.mw_ocean_create(None, None) == mw.native.MW_E_INVALID_ARG
+    assert lib.mw_ocean_generate(None, 0.0, None) == mw.native.MW_E_INVALID_ARG
+    assert lib.mw_ocean_init_spectrum(None) == mw.native.MW_E_INVALID_ARG
+    assert lib.mw_fft2d(0, 64, 1, -1, None, None) == mw.native.MW_E_INVALID_ARG
+    x = np.zeros((48, 48), np.complex64)
+    assert lib.mw_fft2d(0, 48, 1, -1, x.ctypes.data, x.ctypes.data) == mw.native.MW_E_INVALID_ARG
+    assert lib.mw_gerstner_displace(None, None, None, None, 0, 0.0, None) == mw.native.MW_E_INVALID_ARG
+    lib.mw_ocean_destroy(None)  # no-op
+
+
+def test_no_cpu_fallback_without_a_device(mw):
+    """On a box without a GPU the engine must refuse, not compute on the host."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(mw.native.MwError) as ei:
+        mw.Ocean(64)
+    assert ei.value.code == mw.native.MW_E_CUDA
+    g = mw.pond_wave_table_32()
+    with pytest.raises(mw.native.MwError):
+        g.displace(np.zeros((8, 3), np.float32), 0.0)
+
+
+def test_product_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under the package or the C ABI may reference it."""
+    pkg = os.path.join(ROOT, "mistral-water_b200")
+    for dp, _, fns in os.walk(pkg):
+        if os.path.basename(dp) in ("build", "lib", "__pycache__"):
+            continue
+        for fn in fns:
+            if fn.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dp, fn)).read()
+                assert "oracle" not in txt.replace("oracle/ is", ""), f"{fn} mentions the oracle"
+                assert "import cref" not in txt and "ref_fft64" not in txt

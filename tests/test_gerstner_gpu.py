@@ -1,0 +1,94 @@
+"""GPU parity tests of the pond Gerstner path against the literal restatement of
+MistralWaterLib.cginc (oracle/ref_gerstner.c).
+
+Tolerance: the phase theta is formed with the source's own fp32 roundings on both sides, so the only
+difference is sin/cos (MUFU after an exact-ish 3-term reduction, ~5e-7 absolute per wave):
+|delta offset| <= 2e-6 * sum_w (|amp_xz| * |dir| + |amp_y|) + 1 ulp of the vertex coordinate.
+"""
+import numpy as np
+import pytest
+
+from conftest import golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _tol(tab, pos):
+    s = float(np.sum(np.abs(tab[:, 4]) * np.hypot(tab[:, 0], tab[:, 1]) + np.abs(tab[:, 5])))
+    return 2e-6 * s + 1.2e-7 * float(np.abs(pos).max())
+
+
+def test_material_gerstner_matches_literal_4_wave(mw, cref):
+    g = golden("gerstner_pond.npz")
+    pos, t = g["pos"], float(g["t"])
+    gw = mw.GerstnerWaves.from_material(**mw.POND_MATERIAL)
+    out = gw.displace(pos, t)
+    assert np.abs((out - pos) - g["offsets4"]).max() <= _tol(gw.table(), pos)
+    m = mw.POND_MATERIAL
+    lit = cref.gerstner4(pos, t, m["_Amplitude"] * 0.01, m["_Frequency"], m["_Steepness"], m["_WSpeed"],
+                         m["_WDirectionAB"], m["_WDirectionCD"])
+    assert np.abs((out - pos) - lit).max() <= _tol(gw.table(), pos)
+
+
+def test_level_one_matches_literal_5_wave(mw, cref):
+    g = golden("gerstner_pond.npz")
+    pos, t = g["pos"], float(g["t"])
+    gw = mw.GerstnerWaves().append_level_one(0.1, 2.58, 0.99)
+    out = gw.displace(pos, t)
+    assert np.abs((out - pos) - g["offsets5"]).max() <= _tol(gw.table(), pos) + 3e-7
+
+
+def test_single_wave_closed_form(mw):
+    gw = mw.GerstnerWaves().append(1.0, 0.0, 0.5, 2.0, 0.3, 0.7)
+    x = np.linspace(-20, 20, 4097).astype(np.float32)
+    pos = np.stack([x, np.zeros_like(x), 0.3 * x], -1)
+    out = gw.displace(pos, 1.25)
+    th = 0.5 * x.astype(np.float64) + 2.0 * 1.25
+    assert np.abs(out[:, 1] - 0.7 * np.sin(th)).max() <= 3e-6
+    assert np.abs(out[:, 0] - (x + 0.3 * np.cos(th))).max() <= 3e-6
+    assert np.array_equal(out[:, 2], pos[:, 2])  # dir_y = 0: no z offset
+
+
+@pytest.mark.parametrize("n", [0, 1, 3, 4, 5, 1023, 1024, 1025])
+def test_ragged_vertex_counts_and_normals(mw, cref, n):
+    gw = mw.pond_wave_table_32()
+    rng = np.random.default_rng(n)
+    pos = rng.uniform(-100, 100, (n, 3)).astype(np.float32)
+    nrm = np.full((n, 3), 7.0, np.float32)
+    out = gw.displace(pos, 0.3, normals=nrm)
+    ref, rn = cref.gerstner_table(gw.table(), pos, 0.3, want_normal=True) if n else (pos, nrm)
+    if n:
+        assert np.abs(out - ref).max() <= _tol(gw.table(), pos)
+        assert np.array_equal(nrm, rn)  # (0,1,0): MistralWaterLib.cginc:98, :121
+
+
+def test_config4_32_waves_1m_vertices(mw, cref):
+    N = 1024
+    ax = ((np.arange(N) - N // 2).astype(np.float32) + np.float32(0.5))
+    pos = np.zeros((N * N, 3), np.float32)
+    pos[:, 0] = np.repeat(ax, N)
+    pos[:, 2] = np.tile(ax, N)
+    gw = mw.pond_wave_table_32()
+    assert gw.n_waves == 32
+    out = gw.displace(pos, 1.7)
+    sel = np.random.default_rng(0).choice(N * N, 200_000, replace=False)
+    ref = cref.gerstner_table(gw.table(), pos[sel], 1.7)
+    assert np.abs(out[sel] - ref).max() <= _tol(gw.table(), pos)
+    # size-independent property: linearity in the amplitudes (doubling every amplitude doubles the offset)
+    g2 = mw.GerstnerWaves()
+    for w in gw.table():
+        g2.append(w[0], w[1], w[2], w[3], 2 * w[4], 2 * w[5])
+    out2 = g2.displace(pos, 1.7)
+    # (out - pos) is only known to an ulp of the coordinate (|pos| <= 512 -> 6.1e-5)
+    assert np.abs((out2 - pos) - 2 * (out - pos)).max() <= 3 * 6.2e-5
+
+
+def test_device_pointer_mode(mw, cref):
+    import torch
+    gw = mw.pond_wave_table_32(device_ptrs=True)
+    pos = torch.rand(4096, 3, device="cuda") * 64 - 32
+    out = torch.empty_like(pos)
+    gw.displace(pos, 0.9, out=out)
+    torch.cuda.synchronize()
+    ref = cref.gerstner_table(gw.table(), pos.cpu().numpy(), 0.9)
+    assert np.abs(out.cpu().numpy() - ref).max() <= _tol(gw.table(), pos.cpu().numpy())

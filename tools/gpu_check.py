@@ -46,7 +46,34 @@ def check_ocean(N, t, literal=False, seed=1234):
                 print(f"   {k:9s} vs literal relL2={r[0]:.2e} maxabs={r[1]:.2e}")
 
 
+def timing():
+    import torch
+    st = torch.cuda.Stream()
+    for N, tiles in ((256, 1), (256, 64), (1024, 1), (1024, 16), (2048, 1), (2048, 4)):
+        o = mw.Ocean(N, seed=1, tiles=tiles, device_ptrs=True, profile=True)
+        o.set_stream(st.cuda_stream)
+        o.init_spectrum()
+        n2 = N * N * tiles
+        bufs = {"height": torch.empty(n2, device="cuda"), "disp": torch.empty(n2 * 2, device="cuda"),
+                "normal": torch.empty(n2 * 3, device="cuda"), "whitecap": torch.empty(n2, device="cuda")}
+        with torch.cuda.stream(st):
+            for i in range(5): o.generate(0.1 * i, bufs)
+            torch.cuda.synchronize()
+            o.kernel_times(reset=True)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            K = 50
+            e0.record(st)
+            for i in range(K): o.generate(0.016 * i, bufs)
+            e1.record(st); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / K
+        kt, kn = o.kernel_times()
+        print(f"N={N} tiles={tiles}: {ms*1e3:.1f} us/frame  {n2/ms/1e6:.2f} Gpts/s  eff GB/s(44B)={n2*44/ms/1e6:.0f}  rows={kt[0]/max(kn[0],1)*1e3:.1f}us cols={kt[1]/max(kn[1],1)*1e3:.1f}us")
+        o.close()
+
+
 if __name__ == "__main__":
+    if "--timing" in sys.argv:
+        timing(); sys.exit(0)
     for n in (32, 64, 128, 256, 512, 1024, 2048):
         check_fft(n)
     for N in (32, 64, 128, 256, 512, 1024, 2048):
@@ -62,24 +89,5 @@ if __name__ == "__main__":
     out = g.displace(pos, 1.7)
     ref = cref.gerstner_table(g.table(), pos, 1.7)
     print("gerstner32 1M: maxabs", np.abs(out - ref).max(), "max|offs|", np.abs(ref - pos).max())
-    # quick timing, device pointers
-    import torch
-    for N, tiles in ((256, 1), (256, 64), (1024, 1), (1024, 16), (2048, 1), (2048, 4)):
-        o = mw.Ocean(N, seed=1, tiles=tiles, device_ptrs=True, profile=True)
-        o.set_stream(torch.cuda.current_stream().cuda_stream)
-        o.init_spectrum()
-        n2 = N * N * tiles
-        bufs = {"height": torch.empty(n2, device="cuda"), "disp": torch.empty(n2 * 2, device="cuda"),
-                "normal": torch.empty(n2 * 3, device="cuda"), "whitecap": torch.empty(n2, device="cuda")}
-        for i in range(5): o.generate(0.1 * i, bufs)
-        torch.cuda.synchronize()
-        o.kernel_times(reset=True)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        K = 50
-        e0.record()
-        for i in range(K): o.generate(0.016 * i, bufs)
-        e1.record(); torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / K
-        kt, kn = o.kernel_times()
-        print(f"N={N} tiles={tiles}: {ms*1e3:.1f} us/frame  {n2/ms/1e6:.2f} Gpts/s  eff GB/s(44B)={n2*44/ms/1e6:.0f}  rows={kt[0]/max(kn[0],1)*1e3:.1f}us cols={kt[1]/max(kn[1],1)*1e3:.1f}us")
-        o.close()
+    timing()
+
