@@ -6,7 +6,8 @@
 // different:
 //   * a line lives in shared memory and is transformed in 2-3 autosort stages of radix 16 (radix
 //     16 x 16 x N/256), each stage done entirely in registers, with ONE shared-memory exchange
-//     between stages -- instead of log2(N) round trips through memory;
+//     (128-bit accesses) between stages -- instead of log2(N) round trips through memory; the
+//     inter-stage twiddles come from small shared-memory tables;
 //   * every "line" is a PAIR of lines transformed together: Blackwell's packed fp32 instructions
 //     (FADD2 / FMUL2 / FFMA2, PTX add/mul/fma.rn.f32x2) operate on two fp32 lanes per register pair
 //     with scalar / immediate twiddles broadcast to both lanes.  The FP32 lane throughput is the
@@ -135,13 +136,12 @@ __device__ __forceinline__ void dft_all(cpk (&v)[PTS])
 }
 
 // ---------------------------------------------------------------------------------------------
-// shared-memory layout of a packed line: two planes (re pairs, im pairs) of float2, 64-bit accesses
+// shared-memory layout of a packed line: float4 elements (re.x, re.y, im.x, im.y), 128-bit accesses
 // ---------------------------------------------------------------------------------------------
 __host__ __device__ constexpr int pad_idx(int i) { return i + (i >> 4); }
-// plane pitch in float2: room for pad_idx(N-1); a line is two planes, so the line stride is 2 * pitch,
-// which must be == 16/W (mod 16) for the transposing accesses of a W-column slab (lane = column + W * row)
-// to touch 16 distinct 8-byte bank groups per half warp  =>  pitch == 8/W (mod 8)
-__host__ __device__ constexpr int plane_pitch(int n, int w) { return ((n + n / 16 + 15) / 16) * 16 + 8 / w; }
+// line pitch in float4: room for pad_idx(N-1), and == 8/W (mod 8) so that the transposing accesses of a
+// W-column slab (lane = column + W * row) touch 8 distinct 16-byte bank groups per quarter warp
+__host__ __device__ constexpr int line_pitch(int n, int w) { return ((n + n / 16 + 7) / 8) * 8 + 8 / w; }
 
 template <int N>
 struct Plan {
@@ -150,6 +150,14 @@ struct Plan {
     static constexpr int R1 = 16;                               // first radix
     static constexpr int R2 = N / 16 < 16 ? N / 16 : 16;        // second radix
     static constexpr int R3 = N / (16 * R2);                    // third radix (1 => two stages)
+    // twiddle tables kept in shared memory (filled once per CTA by load_twiddles):
+    //   tw2[k][r] = W_{16 R2}^{r k}, k < 16, r < R2: rows of R2 float2 (+ 16 B pad so that the LDS.128 of
+    //               eight lanes with consecutive k are conflict free)
+    //   tw3[k]    = W_N^k, k < 16 R2 (third stage: the powers r = 2.. are formed by multiplication)
+    static constexpr int TW2_ROW = R2 / 2 + 1;                  // float4 per row
+    static constexpr int TW2_F4 = 16 * TW2_ROW;
+    static constexpr int TW3_F2 = R3 > 1 ? 16 * R2 : 0;
+    static constexpr int TW_BYTES = TW2_F4 * 16 + TW3_F2 * 8;
 };
 
 // all T threads of a line group (T <= 32: within one warp; else whole warps on a named barrier)
@@ -159,95 +167,187 @@ __device__ __forceinline__ void group_sync(int line_id)
     if constexpr (T <= 32) {
         __syncwarp();
     } else {
+#ifndef MW_CTA_BARRIERS
         asm volatile("bar.sync %0, %1;" ::"r"(line_id + 1), "n"(T) : "memory");
+#else
+        (void)line_id;
+        __syncthreads();  // every group of the CTA runs the same stage sequence, so a CTA-wide barrier is valid
+#endif
     }
 }
 
-// twiddle table lookup: tw[x] = exp(+2 pi i x / N); SIGN < 0 conjugates.
-template <int SIGN>
-__device__ __forceinline__ float2 tw_get(const float2* __restrict__ tw, int x)
+// Fill the shared twiddle tables from the global table gtw[x] = exp(+2 pi i x / N) (SIGN < 0 conjugates).
+// Every thread of the CTA takes part; the caller's next __syncthreads publishes the tables.
+template <int N, int SIGN>
+__device__ __forceinline__ void load_twiddles(float4* tw2, float2* tw3, const float2* __restrict__ gtw)
 {
-    float2 w = __ldg(tw + x);
-    if constexpr (SIGN < 0) w.y = -w.y;
-    return w;
-}
-
-// A Stockham stage (radix R, S = product of the radices before it) on registers that already hold
-// {line[g + T*c]}.  Applies the stage twiddles, runs the 16/R butterflies and hands every result to
-// `emit(dest_index, value)`.
-template <int N, int SIGN, int R, int S, class Emit>
-__device__ __forceinline__ void stage_regs(cpk (&v)[PTS], int g, const float2* __restrict__ tw, Emit&& emit)
-{
-    constexpr int T = N / PTS;
-    constexpr int B = PTS / R;        // butterflies per thread
-    constexpr int TWS = N / (S * R);  // table stride: W_{S*R} = tw[TWS]
-    if constexpr (S > 1) {
-#pragma unroll
-        for (int b = 0; b < B; ++b) {
-            const int k = (g + b * T) & (S - 1);
-#pragma unroll
-            for (int r = 1; r < R; ++r) {
-                const float2 w = tw_get<SIGN>(tw, r * k * TWS);
-                v[b + r * B] = pmul(v[b + r * B], w.x, w.y);
-            }
+    using P = Plan<N>;
+    float2* t2 = reinterpret_cast<float2*>(tw2);
+    constexpr int TWS2 = N / (16 * P::R2);
+    for (int i = threadIdx.x; i < 16 * P::R2; i += blockDim.x) {
+        const int k = i / P::R2, r = i % P::R2;
+        float2 w = __ldg(gtw + r * k * TWS2);
+        if (SIGN < 0) w.y = -w.y;
+        t2[k * (2 * P::TW2_ROW) + r] = w;
+    }
+    if constexpr (P::R3 > 1) {
+        for (int i = threadIdx.x; i < 16 * P::R2; i += blockDim.x) {
+            float2 w = __ldg(gtw + i);
+            if (SIGN < 0) w.y = -w.y;
+            tw3[i] = w;
         }
     }
-    dft_all<SIGN, R, B>(v);
-    constexpr int LOGR = ilog2(R);
+}
+
+__device__ __forceinline__ float2 cmul_s(float2 a, float2 b)
+{
+    return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
+}
+
+// Padded-index arithmetic without per-element shifts: for a multiple of 16, pad_idx(x + m) = pad_idx(x) +
+// m + m / 16, so every access of a thread is "one base + compile-time offsets" (immediate-offset LDS/STS).
+__host__ __device__ constexpr int pad_step(int m) { return m + m / 16; }
+
+// Hands the R outputs of each of the B butterflies to emit(idx, pidx, value): idx = natural index of the
+// output, pidx = pad_idx(idx) (for emitters that write into a line).
+template <int N, int R, int S, class Emit>
+__device__ __forceinline__ void emit_all(cpk (&v)[PTS], int g, Emit&& emit)
+{
+    constexpr int T = N / PTS, B = PTS / R, LOGR = ilog2(R);
 #pragma unroll
     for (int b = 0; b < B; ++b) {
         const int j = g + b * T;
         const int k = j & (S - 1);
         const int base = (j - k) * R + k;  // (j / S) * S * R + k
+        if constexpr (S % 16 == 0) {
+            const int pbase = pad_idx(base);
 #pragma unroll
-        for (int i = 0; i < R; ++i) emit(base + bitrev(i, LOGR) * S, v[b + i * B]);
+            for (int i = 0; i < R; ++i) {
+                const int rr = bitrev(i, LOGR);
+                emit(base + rr * S, pbase + rr * pad_step(S), v[b + i * B]);
+            }
+        } else {  // S == 1: idx = R j + r with R = 16 here, so idx >> 4 == j
+            static_assert(S == 1 && R == 16, "first stage is radix 16");
+#pragma unroll
+            for (int i = 0; i < R; ++i) {
+                const int rr = bitrev(i, LOGR);
+                emit(base + rr, 17 * j + rr, v[b + i * B]);
+            }
+        }
     }
+}
+
+// Stage 1 (radix 16, no twiddles)
+template <int N, int SIGN, class Emit>
+__device__ __forceinline__ void stage1(cpk (&v)[PTS], int g, Emit&& emit)
+{
+    dft_all<SIGN, 16, 1>(v);
+    emit_all<N, 16, 1>(v, g, emit);
+}
+// Stage 2 (radix R2, S = 16): twiddles W_{16 R2}^{r k}, k = j mod 16, one table row per butterfly
+template <int N, int SIGN, class Emit>
+__device__ __forceinline__ void stage2(cpk (&v)[PTS], int g, const float4* tw2, Emit&& emit)
+{
+    using P = Plan<N>;
+    constexpr int R = P::R2, B = PTS / R, T = P::T;
+#pragma unroll
+    for (int b = 0; b < B; ++b) {
+        const int k = (g + b * T) & 15;
+        const float4* row = tw2 + k * P::TW2_ROW;
+#pragma unroll
+        for (int r2 = 0; r2 < R / 2; ++r2) {
+            const float4 w = row[r2];  // twiddles 2 r2 and 2 r2 + 1
+            if (r2 > 0) v[b + (2 * r2) * B] = pmul(v[b + (2 * r2) * B], w.x, w.y);
+            v[b + (2 * r2 + 1) * B] = pmul(v[b + (2 * r2 + 1) * B], w.z, w.w);
+        }
+    }
+    dft_all<SIGN, R, B>(v);
+    emit_all<N, R, 16>(v, g, emit);
+}
+// Stage 3 (radix R3, S = 16 R2): twiddles W_N^{r k}; w^1 from the table, higher powers by multiplication
+template <int N, int SIGN, class Emit>
+__device__ __forceinline__ void stage3(cpk (&v)[PTS], int g, const float2* tw3, Emit&& emit)
+{
+    using P = Plan<N>;
+    constexpr int R = P::R3, B = PTS / R, T = P::T, S = 16 * P::R2;
+#pragma unroll
+    for (int b = 0; b < B; ++b) {
+        const int k = (g + b * T) & (S - 1);
+        float2 pw[R];
+        pw[1] = tw3[k];
+#pragma unroll
+        for (int r = 2; r < R; ++r) pw[r] = cmul_s(pw[r / 2], pw[r - r / 2]);
+#pragma unroll
+        for (int r = 1; r < R; ++r) v[b + r * B] = pmul(v[b + r * B], pw[r].x, pw[r].y);
+    }
+    dft_all<SIGN, R, B>(v);
+    emit_all<N, R, S>(v, g, emit);
 }
 
 template <int N>
-__device__ __forceinline__ void load_line_regs(cpk (&v)[PTS], const float2* pre, const float2* pim, int g)
+__device__ __forceinline__ void load_line_regs(cpk (&v)[PTS], const float4* line, int g)
 {
     constexpr int T = N / PTS;
+    if constexpr (T % 16 == 0) {
+        const float4* p = line + pad_idx(g);
 #pragma unroll
-    for (int c = 0; c < PTS; ++c) {
-        const int p = pad_idx(g + T * c);
-        v[c].re = pre[p];
-        v[c].im = pim[p];
+        for (int c = 0; c < PTS; ++c) {
+            const float4 e = p[c * pad_step(T)];
+            v[c].re = make_float2(e.x, e.y);
+            v[c].im = make_float2(e.z, e.w);
+        }
+    } else {
+#pragma unroll
+        for (int c = 0; c < PTS; ++c) {
+            const float4 e = line[pad_idx(g + T * c)];
+            v[c].re = make_float2(e.x, e.y);
+            v[c].im = make_float2(e.z, e.w);
+        }
     }
 }
 
-// Full transform of one packed line held in shared memory (planes `pre`, `pim`, padded with pad_idx),
-// by the T threads of its group (g = index within the group, line_id = barrier id of the group).
-// `active` = this group has a real line; inactive groups still arrive at their barrier.  The final
-// stage's results go to `emit(index, value)` in natural order; emit may write into the line itself
-// (every read of the group is complete before the first emit).
+// Full transform of one packed line held in shared memory (`line`, padded with pad_idx), by the T
+// threads of its group (g = index within the group, line_id = barrier id of the group).  `active` =
+// this group has a real line; inactive groups still arrive at their barrier.  The final stage's
+// results go to `emit(idx, pidx, value)` in natural order (pidx = pad_idx(idx)); emit may write into
+// the line itself (every read of the group is complete before the first emit).
 template <int N, int SIGN, class Emit>
-__device__ __forceinline__ void fft_line(float2* pre, float2* pim, int g, int line_id, bool active,
-                                         const float2* __restrict__ tw, Emit&& emit)
+__device__ __forceinline__ void fft_line(float4* line, int g, int line_id, bool active, const float4* tw2,
+                                         const float2* tw3, Emit&& emit)
 {
     using P = Plan<N>;
     constexpr int T = P::T;
+    constexpr int NSYNC = P::R3 == 1 ? 3 : 5;
+    if (!active) {  // keep the barrier protocol, touch nothing (straight-line code for the active path)
+#pragma unroll
+        for (int i = 0; i < NSYNC; ++i) group_sync<T>(line_id);
+        return;
+    }
     cpk v[PTS];
-    auto to_smem = [&](int idx, cpk val) {
-        const int p = pad_idx(idx);
-        pre[p] = val.re;
-        pim[p] = val.im;
-    };
-    if (active) load_line_regs<N>(v, pre, pim, g);
+    auto to_smem = [&](int, int pidx, cpk val) { line[pidx] = make_float4(val.re.x, val.re.y, val.im.x, val.im.y); };
+    load_line_regs<N>(v, line, g);
     group_sync<T>(line_id);  // everyone has read before anyone overwrites (in-place exchange)
-    if (active) stage_regs<N, SIGN, P::R1, 1>(v, g, tw, to_smem);
+    stage1<N, SIGN>(v, g, to_smem);
     group_sync<T>(line_id);
-    if (active) load_line_regs<N>(v, pre, pim, g);
+    load_line_regs<N>(v, line, g);
     group_sync<T>(line_id);
     if constexpr (P::R3 == 1) {
-        if (active) stage_regs<N, SIGN, P::R2, P::R1>(v, g, tw, emit);
+        stage2<N, SIGN>(v, g, tw2, emit);
     } else {
-        if (active) stage_regs<N, SIGN, P::R2, P::R1>(v, g, tw, to_smem);
+        stage2<N, SIGN>(v, g, tw2, to_smem);
         group_sync<T>(line_id);
-        if (active) load_line_regs<N>(v, pre, pim, g);
+        load_line_regs<N>(v, line, g);
         group_sync<T>(line_id);
-        if (active) stage_regs<N, SIGN, P::R3, P::R1 * P::R2>(v, g, tw, emit);
+        stage3<N, SIGN>(v, g, tw3, emit);
     }
 }
+
+// 16-byte asynchronous global -> shared copy (LDGSTS, L2 only: the data is streamed once)
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory"); }
 
 }  // namespace mwfft

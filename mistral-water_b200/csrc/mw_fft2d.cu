@@ -16,75 +16,75 @@ using mwfft::pad_idx;
 // LR packed lines per CTA; packed line l holds rows 2l and 2l+1 (contiguous along the transform direction).
 template <int N, int LR, int SIGN>
 __global__ void __launch_bounds__(LR * (N / 16)) k_fft_rows(const float2* __restrict__ in, float2* __restrict__ out,
-                                                           const float2* __restrict__ tw, int lines_total)
+                                                           const float2* __restrict__ gtw, int lines_total)
 {
     using P = Plan<N>;
     constexpr int T = P::T;
-    constexpr int PITCH = mwfft::plane_pitch(N, 8);
-    extern __shared__ float2 smem[];
+    constexpr int LP = mwfft::line_pitch(N, 8);
+    extern __shared__ float4 smem4[];
+    float4* tw2 = smem4;
+    float2* tw3 = reinterpret_cast<float2*>(smem4 + P::TW2_F4);
     const int lr = threadIdx.x / T, g = threadIdx.x % T;
-    const int line = blockIdx.x * LR + lr;
-    const bool active = line < lines_total;
-    float2* pre = smem + 2 * lr * PITCH;
-    float2* pim = pre + PITCH;
-    const float2* s0 = in + (size_t)(2 * line) * N;
+    const int ln = blockIdx.x * LR + lr;
+    const bool active = ln < lines_total;
+    float4* line = smem4 + P::TW_BYTES / 16 + lr * LP;
+    mwfft::load_twiddles<N, SIGN>(tw2, tw3, gtw);
+    const float2* s0 = in + (size_t)(2 * ln) * N;
     const float2* s1 = s0 + N;
     if (active) {
 #pragma unroll
         for (int c = 0; c < 16; ++c) {
             const int i = g + T * c;
             const float2 a = s0[i], b = s1[i];
-            pre[pad_idx(i)] = make_float2(a.x, b.x);
-            pim[pad_idx(i)] = make_float2(a.y, b.y);
+            line[pad_idx(i)] = make_float4(a.x, b.x, a.y, b.y);
         }
     }
     __syncthreads();
-    float2* d0 = out + (size_t)(2 * line) * N;
+    float2* d0 = out + (size_t)(2 * ln) * N;
     float2* d1 = d0 + N;
-    mwfft::fft_line<N, SIGN>(pre, pim, g, lr, active, tw, [&](int idx, mwfft::cpk v) {
+    mwfft::fft_line<N, SIGN>(line, g, lr, active, tw2, tw3, [&](int idx, int, mwfft::cpk v) {
         d0[idx] = make_float2(v.re.x, v.im.x);
         d1[idx] = make_float2(v.re.y, v.im.y);
     });
 }
 
-// Slab of W columns per CTA (W/2 packed lines): transposing load, FFT along the strided direction,
+// Slab of 8 columns per CTA (4 packed lines): transposing load, FFT along the strided direction,
 // transposing store.
-template <int N, int W, int SIGN>
-__global__ void __launch_bounds__((W / 2) * (N / 16)) k_fft_cols(const float2* __restrict__ in, float2* __restrict__ out,
-                                                                const float2* __restrict__ tw)
+template <int N, int SIGN>
+__global__ void __launch_bounds__(4 * (N / 16)) k_fft_cols(const float2* __restrict__ in, float2* __restrict__ out,
+                                                          const float2* __restrict__ gtw)
 {
     using P = Plan<N>;
     constexpr int T = P::T;
-    constexpr int HL = W / 2;
-    constexpr int MAIN = HL * T;
-    constexpr int PITCH = mwfft::plane_pitch(N, HL);
-    extern __shared__ float2 smem[];
+    constexpr int MAIN = 4 * T;
+    constexpr int LP = mwfft::line_pitch(N, 4);
+    extern __shared__ float4 smem4[];
+    float4* tw2 = smem4;
+    float2* tw3 = reinterpret_cast<float2*>(smem4 + P::TW2_F4);
+    float4* lines = smem4 + P::TW_BYTES / 16;
     const int tid = threadIdx.x;
     const int q = tid / T, g = tid % T;
-    const int b0 = blockIdx.x * W;
+    const int b0 = blockIdx.x * 8;
     const size_t base = (size_t)blockIdx.y * N * N;
+    mwfft::load_twiddles<N, SIGN>(tw2, tw3, gtw);
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
         const int e = tid + k * MAIN;
-        const int n = e / HL, c2 = e % HL;
+        const int n = e >> 2, c2 = e & 3;
         const float4 v = *reinterpret_cast<const float4*>(in + base + (size_t)n * N + b0 + 2 * c2);
-        smem[2 * c2 * PITCH + pad_idx(n)] = make_float2(v.x, v.z);
-        smem[(2 * c2 + 1) * PITCH + pad_idx(n)] = make_float2(v.y, v.w);
+        lines[c2 * LP + pad_idx(n)] = make_float4(v.x, v.z, v.y, v.w);
     }
     __syncthreads();
-    float2* pre = smem + 2 * q * PITCH;
-    float2* pim = pre + PITCH;
-    mwfft::fft_line<N, SIGN>(pre, pim, g, q, true, tw, [&](int idx, mwfft::cpk v) {
-        pre[pad_idx(idx)] = v.re;
-        pim[pad_idx(idx)] = v.im;
+    float4* line = lines + q * LP;
+    mwfft::fft_line<N, SIGN>(line, g, q, true, tw2, tw3, [&](int, int pidx, mwfft::cpk v) {
+        line[pidx] = make_float4(v.re.x, v.im.x, v.re.y, v.im.y);
     });
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
         const int e = tid + k * MAIN;
-        const int n = e / HL, c2 = e % HL;
-        const float2 r = smem[2 * c2 * PITCH + pad_idx(n)], i = smem[(2 * c2 + 1) * PITCH + pad_idx(n)];
-        *reinterpret_cast<float4*>(out + base + (size_t)n * N + b0 + 2 * c2) = make_float4(r.x, i.x, r.y, i.y);
+        const int n = e >> 2, c2 = e & 3;
+        *reinterpret_cast<float4*>(out + base + (size_t)n * N + b0 + 2 * c2) = lines[c2 * LP + pad_idx(n)];
     }
 }
 
@@ -93,15 +93,14 @@ int run2d(int batch, const float2* d_in, float2* d_tmp, float2* d_out, const flo
 {
     constexpr int T = N / 16;
     constexpr int LR = (T >= 64) ? 2 : (128 / T);
-    constexpr int W = 8;
-    constexpr size_t smem_r = (size_t)LR * 2 * mwfft::plane_pitch(N, 8) * sizeof(float2);
-    constexpr size_t smem_c = (size_t)(W / 2) * 2 * mwfft::plane_pitch(N, W / 2) * sizeof(float2);
+    constexpr size_t smem_r = Plan<N>::TW_BYTES + (size_t)LR * mwfft::line_pitch(N, 8) * sizeof(float4);
+    constexpr size_t smem_c = Plan<N>::TW_BYTES + (size_t)4 * mwfft::line_pitch(N, 4) * sizeof(float4);
     MW_CUDA(cudaFuncSetAttribute(k_fft_rows<N, LR, SIGN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r));
-    MW_CUDA(cudaFuncSetAttribute(k_fft_cols<N, W, SIGN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
+    MW_CUDA(cudaFuncSetAttribute(k_fft_cols<N, SIGN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
     const int lines_total = batch * N / 2;
     k_fft_rows<N, LR, SIGN><<<(lines_total + LR - 1) / LR, LR * T, smem_r, st>>>(d_in, d_tmp, d_tw, lines_total);
     MW_LAUNCH_CHECK();
-    k_fft_cols<N, W, SIGN><<<dim3(N / W, batch), (W / 2) * T, smem_c, st>>>(d_tmp, d_out, d_tw);
+    k_fft_cols<N, SIGN><<<dim3(N / 8, batch), 4 * T, smem_c, st>>>(d_tmp, d_out, d_tw);
     MW_LAUNCH_CHECK();
     return MW_OK;
 }

@@ -50,6 +50,8 @@ struct mw_ocean {
     // scratch outputs (host-pointer mode, or inputs of k_mesh_outputs)
     float* s_height = nullptr; float2* s_disp = nullptr; float* s_normal = nullptr; float* s_white = nullptr;
     float* s_jac = nullptr; float* s_vert = nullptr; float4* s_col = nullptr; float2* s_h = nullptr;
+    int dbg_flags = 0;
+    long long* dbg_rows = nullptr; long long* dbg_cols = nullptr;  // developer phase timing (mw_debug_phase_buffers)
     // profiling
     std::vector<EvPair> ev_pool; size_t ev_used = 0;
     double k_ms[MW_KERNEL_COUNT] = {0, 0, 0};
@@ -331,7 +333,7 @@ template <int N, int RP, int MINB>
 static int launch_rows(mw_ocean* o, const mwk::RowArgs& a)
 {
     constexpr int threads = RP * 3 * (N / 16);
-    constexpr size_t smem = (size_t)RP * 6 * mwfft::plane_pitch(N, 8) * sizeof(float2);
+    constexpr size_t smem = mwfft::Plan<N>::TW_BYTES + (size_t)RP * 3 * mwfft::line_pitch(N, 8) * sizeof(float4);
     static bool attr_done[64] = {};
     if (!attr_done[o->p.device]) {
         MW_CUDA(cudaFuncSetAttribute(mwk::k_spectrum_rows<N, RP, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -346,21 +348,25 @@ static int launch_rows(mw_ocean* o, const mwk::RowArgs& a)
     return MW_OK;
 }
 
-template <int N, int W, int MINB>
-static int launch_cols(mw_ocean* o, const mwk::ColArgs& a)
+template <int N, int MINB>
+static int launch_cols(mw_ocean* o, mwk::ColArgs a)
 {
-    constexpr int threads = (W + 1) * (N / 16);
-    constexpr size_t smem = (size_t)(W + 1) * 2 * mwfft::plane_pitch(N, W) * sizeof(float2);
+    constexpr int threads = 5 * (N / 16);
+    constexpr size_t smem = mwfft::Plan<N>::TW_BYTES + (size_t)5 * mwfft::line_pitch(N, 4) * sizeof(float4);
     static bool attr_done[64] = {};
     if (!attr_done[o->p.device]) {
-        MW_CUDA(cudaFuncSetAttribute(mwk::k_cols_extract<N, W, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        MW_CUDA(cudaFuncSetAttribute(mwk::k_cols_extract<N, W, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout,
+        MW_CUDA(cudaFuncSetAttribute(mwk::k_cols_extract<N, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        MW_CUDA(cudaFuncSetAttribute(mwk::k_cols_extract<N, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                      cudaSharedmemCarveoutMaxShared));
         attr_done[o->p.device] = true;
     }
-    dim3 grid(N / W, o->tiles);
+    const bool want_ab = a.disp || a.normal || a.whitecap || a.jacobian;
+    a.ab_blocks = want_ab ? N / 4 : 0;
+    const int c_blocks = a.height ? N / 8 : 0;
+    if (a.ab_blocks + c_blocks == 0) return MW_OK;
+    dim3 grid(a.ab_blocks + c_blocks, o->tiles);
     ProfScope ps(o, 1);
-    mwk::k_cols_extract<N, W, MINB><<<grid, threads, smem, o->stream>>>(a);
+    mwk::k_cols_extract<N, MINB><<<grid, threads, smem, o->stream>>>(a);
     MW_LAUNCH_CHECK();
     return MW_OK;
 }
@@ -369,17 +375,17 @@ static int run_frame(mw_ocean* o, const mwk::RowArgs& ra, const mwk::ColArgs& ca
 {
     int rc;
     switch (o->N) {
-#define MW_CASE(N_, RP_, RMINB_, W_, CMINB_)                                  \
+#define MW_CASE(N_, RP_, RMINB_, CMINB_)                                      \
     case N_:                                                                  \
         if ((rc = launch_rows<N_, RP_, RMINB_>(o, ra))) return rc;            \
-        return launch_cols<N_, W_, CMINB_>(o, ca);
-        MW_CASE(32, 16, 1, 4, 1)
-        MW_CASE(64, 8, 1, 4, 1)
-        MW_CASE(128, 8, 1, 4, 1)
-        MW_CASE(256, 4, 2, 4, 2)
-        MW_CASE(512, 2, 2, 4, 2)
-        MW_CASE(1024, 1, 3, 4, 2)
-        MW_CASE(2048, 1, 1, 4, 1)
+        return launch_cols<N_, CMINB_>(o, ca);
+        MW_CASE(32, 16, 1, 1)
+        MW_CASE(64, 8, 1, 1)
+        MW_CASE(128, 8, 1, 1)
+        MW_CASE(256, 4, 2, 2)
+        MW_CASE(512, 2, 2, 2)
+        MW_CASE(1024, 1, 3, 2)
+        MW_CASE(2048, 1, 1, 1)
 #undef MW_CASE
     }
     mw_set_error("unsupported resolution %d", o->N);
@@ -419,8 +425,8 @@ extern "C" int mw_ocean_generate(mw_ocean* o, float t, const mw_ocean_out* out)
         else { if ((rc = ensure(&o->s_jac, total))) return rc; d_jac = o->s_jac; }
     }
 
-    mwk::RowArgs ra{o->spec, o->omega, o->ramp, o->kd, o->tw, o->XAB, o->XC, t};
-    mwk::ColArgs ca{o->XAB, o->XC, o->tw, d_height, d_disp, d_normal, d_white, d_jac};
+    mwk::RowArgs ra{o->spec, o->omega, o->ramp, o->kd, o->tw, o->XAB, o->XC, t, o->dbg_rows, o->dbg_flags};
+    mwk::ColArgs ca{o->XAB, o->XC, o->tw, d_height, d_disp, d_normal, d_white, d_jac, o->dbg_cols, o->dbg_flags, 0};
     if ((rc = run_frame(o, ra, ca))) return rc;
 
     float* d_vert = nullptr; float4* d_col = nullptr;
@@ -480,5 +486,20 @@ extern "C" int mw_ocean_kernel_times(mw_ocean* o, float ms[MW_KERNEL_COUNT], int
         if (launches) launches[k] = o->k_n[k];
         if (reset) { o->k_ms[k] = 0; o->k_n[k] = 0; }
     }
+    return MW_OK;
+}
+
+// Developer hook (not in the public header): device buffers that receive 8 clock64 stamps per CTA.
+extern "C" __attribute__((visibility("default"))) int mw_debug_phase_buffers(mw_ocean* o, long long* rows, long long* cols)
+{
+    if (!o) return MW_E_INVALID_ARG;
+    o->dbg_rows = rows;
+    o->dbg_cols = cols;
+    return MW_OK;
+}
+extern "C" __attribute__((visibility("default"))) int mw_debug_flags(mw_ocean* o, int flags)
+{
+    if (!o) return MW_E_INVALID_ARG;
+    o->dbg_flags = flags;
     return MW_OK;
 }

@@ -151,6 +151,8 @@ struct RowArgs {
     float4* XAB;           // [tiles][N][N]
     float2* XC;            // [tiles][N][N]
     float t;
+    long long* dbg;        // developer phase-timing buffer (NULL in production)
+    int dbg_flags;         // developer experiments: 1 = no output stores, 2 = no FFT, 4 = no spectrum loads
 };
 
 // F[n,m] = (p1 * e1 - p2 * conj(e2)) * (-i/2): the Hermitian "imaginary part" packing of SURVEY 3.4
@@ -160,6 +162,16 @@ __device__ __forceinline__ float2 herm_pack(float2 p1, float2 e1, float2 p2, flo
     return make_float2(0.5f * d.y, -0.5f * d.x);
 }
 
+// Signs.  The direct sum equals sigma[a,b] * T[a,b] with sigma = -(-1)^(a+b), and Dz carries an
+// extra minus (FFTMesh.cs:215).  None of that costs an instruction here:
+//   * (-1)^b : pass 1 stores spectrum element m at line position (m + N/2) mod N   (shift theorem);
+//   * (-1)^a : pass 2 stores intermediate row n at line position (n + N/2) mod N;
+//   * the remaining constant signs go into the packing multipliers below, chosen so that the finished
+//     transforms ARE the outputs:  A' -> (dx + i dz),  B' -> (sx + i sz),  C' -> height (real part).
+//       A' = -Im-part(ux Hc) + i Im-part(uz Hc)   => multiplier (-ux + i uz)
+//       B' = -Im-part(kx H)  - i Im-part(kz H)    => multiplier (-kx - i kz)
+//       C' = -H
+
 // RP row pairs per CTA; 3 packed lines per pair: (A,B) of row rA, (A,B) of row rB, (C of rA, C of rB).
 template <int N, int RP, int MINB>
 __global__ void __launch_bounds__(RP * 3 * (N / 16), MINB) k_spectrum_rows(const RowArgs a)
@@ -167,14 +179,21 @@ __global__ void __launch_bounds__(RP * 3 * (N / 16), MINB) k_spectrum_rows(const
     using P = Plan<N>;
     constexpr int T = P::T;
     constexpr int PAIR_THREADS = 3 * T;
-    constexpr int PITCH = mwfft::plane_pitch(N, 8);
-    extern __shared__ float2 smem[];
+    constexpr int LP = mwfft::line_pitch(N, 8);
+    extern __shared__ float4 smem4[];
+    float4* tw2 = smem4;
+    float2* tw3 = reinterpret_cast<float2*>(smem4 + P::TW2_F4);
+    float4* all_lines = smem4 + P::TW_BYTES / 16;
 
     const int tile = blockIdx.y;
     const int rp = threadIdx.x / PAIR_THREADS;
     const int lt = threadIdx.x % PAIR_THREADS;
     const int pair = blockIdx.x * RP + rp;  // < N/2
-    float2* lines = smem + rp * 6 * PITCH;  // line q: re plane at (2q) * PITCH, im plane at (2q+1) * PITCH
+    float4* lines = all_lines + rp * 3 * LP;
+
+    mwfft::load_twiddles<N, +1>(tw2, tw3, a.tw);
+#define MW_RSTAMP(i) do { if (a.dbg && threadIdx.x == 0) a.dbg[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 8 + (i)] = clock64(); } while (0)
+    MW_RSTAMP(0);
 
     const bool special = pair == 0;         // rows 0 and N/2 mirror onto themselves
     const int rA = special ? 0 : pair;
@@ -184,7 +203,8 @@ __global__ void __launch_bounds__(RP * 3 * (N / 16), MINB) k_spectrum_rows(const
 
     // ---- evolve + pack.  One task = the four grid points (rA|rB, m|m') with m' = -m mod N; the set is
     //      closed under k -> -k, so every Hermitian partner is on hand and every point is read once. ----
-    for (int m = lt; m <= N / 2; m += PAIR_THREADS) {
+    if (a.dbg_flags & 512) return;
+    for (int m = lt; m <= N / 2 && !(a.dbg_flags & 32); m += PAIR_THREADS) {
         const int mm = (N - m) & (N - 1);
         const float4 s1 = ldg_stream4(spec + rA * N + m);    // P1 = (rA, m)
         const float4 s2 = ldg_stream4(spec + rB * N + mm);   // P2 = (rB, m')
@@ -206,9 +226,10 @@ __global__ void __launch_bounds__(RP * 3 * (N / 16), MINB) k_spectrum_rows(const
         const float k2A = kxA * kxA + kzm * kzm, k2B = kxB * kxB + kzm * kzm;
         const float invA = k2A < MW_EPSILON_F * MW_EPSILON_F ? 0.0f : rsqrtf(k2A);  // FFTMesh.cs:213-214
         const float invB = k2B < MW_EPSILON_F * MW_EPSILON_F ? 0.0f : rsqrtf(k2B);
-        const float2 k1 = make_float2(kxA, kzm), k2 = make_float2(kxB, kzmm), k3 = make_float2(kxA, kzmm), k4 = make_float2(kxB, kzm);
-        const float2 u1 = make_float2(k1.x * invA, k1.y * invA), u3 = make_float2(k3.x * invA, k3.y * invA);
-        const float2 u2 = make_float2(k2.x * invB, k2.y * invB), u4 = make_float2(k4.x * invB, k4.y * invB);
+        // packing multipliers with the output signs folded in (see "Signs" above)
+        const float2 k1 = make_float2(-kxA, -kzm), k2 = make_float2(-kxB, -kzmm), k3 = make_float2(-kxA, -kzmm), k4 = make_float2(-kxB, -kzm);
+        const float2 u1 = make_float2(-kxA * invA, kzm * invA), u3 = make_float2(-kxA * invA, kzmm * invA);
+        const float2 u2 = make_float2(-kxB * invB, kzmm * invB), u4 = make_float2(-kxB * invB, kzm * invB);
         float2 A1, A2, A3, A4, B1, B2, B3, B4;
         if (!special) {  // partners: P1 <-> P2, P3 <-> P4
             A1 = herm_pack(u1, E1, u2, E2); A2 = herm_pack(u2, E2, u1, E1);
@@ -221,34 +242,38 @@ __global__ void __launch_bounds__(RP * 3 * (N / 16), MINB) k_spectrum_rows(const
             B1 = herm_pack(k1, E1, k3, E3); B3 = herm_pack(k3, E3, k1, E1);
             B4 = herm_pack(k4, E4, k2, E2); B2 = herm_pack(k2, E2, k4, E4);
         }
-        const int pm = pad_idx(m), pmm = pad_idx(mm);
+        // line positions shifted by N/2: the transform then carries the (-1)^b of sigma
+        const int pm = pad_idx((m + N / 2) & (N - 1)), pmm = pad_idx((mm + N / 2) & (N - 1));
         // line 0 = (A,B) of row rA ; line 1 = (A,B) of row rB ; line 2 = (C of rA, C of rB)
-        lines[0 * PITCH + pm] = make_float2(A1.x, B1.x);  lines[1 * PITCH + pm] = make_float2(A1.y, B1.y);
-        lines[0 * PITCH + pmm] = make_float2(A3.x, B3.x); lines[1 * PITCH + pmm] = make_float2(A3.y, B3.y);
-        lines[2 * PITCH + pm] = make_float2(A4.x, B4.x);  lines[3 * PITCH + pm] = make_float2(A4.y, B4.y);
-        lines[2 * PITCH + pmm] = make_float2(A2.x, B2.x); lines[3 * PITCH + pmm] = make_float2(A2.y, B2.y);
-        lines[4 * PITCH + pm] = make_float2(E1.x, E4.x);  lines[5 * PITCH + pm] = make_float2(E1.y, E4.y);
-        lines[4 * PITCH + pmm] = make_float2(E3.x, E2.x); lines[5 * PITCH + pmm] = make_float2(E3.y, E2.y);
+        lines[pm] = make_float4(A1.x, B1.x, A1.y, B1.y);
+        lines[pmm] = make_float4(A3.x, B3.x, A3.y, B3.y);
+        lines[LP + pm] = make_float4(A4.x, B4.x, A4.y, B4.y);
+        lines[LP + pmm] = make_float4(A2.x, B2.x, A2.y, B2.y);
+        lines[2 * LP + pm] = make_float4(-E1.x, -E4.x, -E1.y, -E4.y);
+        lines[2 * LP + pmm] = make_float4(-E3.x, -E2.x, -E3.y, -E2.y);
     }
+    MW_RSTAMP(1);
     __syncthreads();
+    MW_RSTAMP(2);
 
     // ---- row FFT of the three packed lines ----
     const int q = lt / T, g = lt % T;
-    float2* pre = lines + 2 * q * PITCH;
-    float2* pim = pre + PITCH;
+    float4* line = lines + q * LP;
     const size_t tbase = (size_t)tile * N * N;
+    if (a.dbg_flags & 64) return;
     if (q < 2) {
         float4* dst = a.XAB + tbase + (size_t)(q ? rB : rA) * N;
-        mwfft::fft_line<N, +1>(pre, pim, g, rp * 3 + q, true, a.tw,
-                               [&](int idx, mwfft::cpk v) { dst[idx] = make_float4(v.re.x, v.re.y, v.im.x, v.im.y); });
+        mwfft::fft_line<N, +1>(line, g, rp * 3 + q, true, tw2, tw3,
+                               [&](int idx, int, mwfft::cpk v) { dst[idx] = make_float4(v.re.x, v.re.y, v.im.x, v.im.y); });
     } else {
         float2* dA = a.XC + tbase + (size_t)rA * N;
         float2* dB = a.XC + tbase + (size_t)rB * N;
-        mwfft::fft_line<N, +1>(pre, pim, g, rp * 3 + q, true, a.tw, [&](int idx, mwfft::cpk v) {
+        mwfft::fft_line<N, +1>(line, g, rp * 3 + q, true, tw2, tw3, [&](int idx, int, mwfft::cpk v) {
             dA[idx] = make_float2(v.re.x, v.im.x);
             dB[idx] = make_float2(v.re.y, v.im.y);
         });
     }
+    MW_RSTAMP(3);
 }
 
 // =============================================================================================
@@ -263,104 +288,123 @@ struct ColArgs {
     float* normal;      // [tiles][N*N][3]  or NULL
     float* whitecap;    // [tiles][N*N]     or NULL
     float* jacobian;    // [tiles][N*N]     or NULL
+    long long* dbg;     // developer phase-timing buffer (NULL in production): 8 clock64 stamps per CTA
+    int dbg_flags;      // developer experiments (tools/phase_timing.py)
+    int ab_blocks;      // blockIdx.x <  ab_blocks : (A,B) slab of 4 columns  (0 if no A/B output is wanted)
+                        // blockIdx.x >= ab_blocks : C slab of 8 columns
 };
 
-// Slab of W columns per CTA, W + 1 packed-line thread groups.
-//   phase 1: the (A,B) pairs of the W columns + the halo column b0 + W (so that hds[index + 1] of
-//            FFTMesh.cs:266 is on chip)  -> hds, normal, Jacobian, whitecap
-//   phase 2: the C field of the W columns, two columns per packed line  -> height
-template <int N, int W, int MINB>
-__global__ void __launch_bounds__((W + 1) * (N / 16), MINB) k_cols_extract(const ColArgs a)
+// 5 packed-line thread groups per CTA, two kinds of CTA in one launch:
+//   (A,B) CTA: the (A,B) pairs of 4 columns + the halo column b0 + 4 (so that hds[index + 1] of
+//              FFTMesh.cs:266 is on chip)  -> hds, normal, Jacobian, whitecap
+//   C CTA    : the C field of 8 columns, two columns per packed line (4 groups busy)  -> height
+// The slab goes global -> shared with 16-byte cp.async straight into its transposed place (the element
+// formats of XAB and of the packed line are the same 16 bytes), so the load costs no registers.
+template <int N, int MINB>
+__global__ void __launch_bounds__(5 * (N / 16), MINB) k_cols_extract(const ColArgs a)
 {
     using P = Plan<N>;
     constexpr int T = P::T;
-    constexpr int MAIN = W * T;  // threads that own the W real columns
-    constexpr int PITCH = mwfft::plane_pitch(N, W);
-    constexpr int LOGW = mwfft::ilog2(W);
-    extern __shared__ float2 smem[];  // line q: re plane at (2q) * PITCH, im plane at (2q+1) * PITCH
+    constexpr int W = 4;
+    constexpr int LP = mwfft::line_pitch(N, W);
+    constexpr int RS = 4 * T / W;                   // row step of the 4-column thread mapping (= T)
+    constexpr int PRS = mwfft::pad_step(RS);        // ... in padded line positions (T % 16 == 0 for N >= 256)
+    constexpr bool LINEAR = (T % 16 == 0);
+    extern __shared__ float4 smem4[];
+    float4* tw2 = smem4;
+    float2* tw3 = reinterpret_cast<float2*>(smem4 + P::TW2_F4);
+    float4* lines = smem4 + P::TW_BYTES / 16;  // [5][LP]
 
     const int tile = blockIdx.y;
-    const int b0 = blockIdx.x * W;
     const int tid = threadIdx.x;
     const int q = tid / T, g = tid % T;
     const bool is_halo = q == W;
     const size_t plane = (size_t)N * N;
     const size_t obase = (size_t)tile * plane;
-    const bool want_white = a.whitecap != nullptr || a.jacobian != nullptr;
-    const bool halo_live = want_white && b0 + W < N;
+    // padded position of row n, and of row (n + N/2) mod N where the loads put it (the (-1)^a of sigma)
+    auto ppos = [](int n) { return pad_idx(n); };
+    auto spos = [](int n) { return pad_idx((n + N / 2) & (N - 1)); };
 
-    // ------------------------------------------------------------------ phase 1: (A, B)
-    if (a.disp || a.normal || want_white) {
+    mwfft::load_twiddles<N, +1>(tw2, tw3, a.tw);
+#define MW_STAMP(i) do { if (a.dbg && tid == 0) a.dbg[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 8 + (i)] = clock64(); } while (0)
+    MW_STAMP(0);
+    if (a.dbg_flags & 256) return;
+
+    if ((int)blockIdx.x < a.ab_blocks) {
+        // ------------------------------------------------------------------ (A, B) slab
+        const int b0 = blockIdx.x * W;
+        const bool want_white = a.whitecap != nullptr || a.jacobian != nullptr;
+        const bool halo_live = want_white && b0 + W < N;
         const float4* X = a.XAB + obase;
-        if (!is_halo) {
-            float4 v[16];
-#pragma unroll
-            for (int k = 0; k < 16; ++k) {
-                const int e = tid + k * MAIN;
-                v[k] = __ldg(X + (size_t)(e >> LOGW) * N + b0 + (e & (W - 1)));
-            }
-#pragma unroll
-            for (int k = 0; k < 16; ++k) {
-                const int e = tid + k * MAIN;
-                const int o = 2 * (e & (W - 1)) * PITCH + pad_idx(e >> LOGW);
-                smem[o] = make_float2(v[k].x, v[k].y);
-                smem[o + PITCH] = make_float2(v[k].z, v[k].w);
-            }
-        } else if (halo_live) {
-#pragma unroll
-            for (int k = 0; k < 16; ++k) {
-                const int n = g + k * T;
-                const float4 h = __ldg(X + (size_t)n * N + b0 + W);
-                smem[2 * W * PITCH + pad_idx(n)] = make_float2(h.x, h.y);
-                smem[(2 * W + 1) * PITCH + pad_idx(n)] = make_float2(h.z, h.w);
-            }
-        }
-        __syncthreads();
         {
-            float2* pre = smem + 2 * q * PITCH;
-            float2* pim = pre + PITCH;
-            const int b = b0 + q;
-            // sigma[a,b] = -(-1)^(a+b); lane x = field A -> (dx, dz) with Dz's extra minus (FFTMesh.cs:215),
-            // lane y = field B -> (sx, sz).  Stored back as re plane = (dx, sx), im plane = (dz, sz).
-            mwfft::fft_line<N, +1>(pre, pim, g, q, !is_halo || halo_live, a.tw, [&](int idx, mwfft::cpk v) {
-                const float s = ((idx + b) & 1) ? 1.0f : -1.0f;
-                const int p = pad_idx(idx);
-                pre[p] = make_float2(s * v.re.x, s * v.re.y);
-                pim[p] = make_float2(-s * v.im.x, s * v.im.y);
-            });
+            // all 5 T threads: thread <-> (row n0 = tid / 5 + T k, column c = tid % 5); a row's 5 elements
+            // (4 slab columns + the halo column) are 80 contiguous bytes
+            const int n0 = tid / 5, c = tid - 5 * n0;
+            if ((c < W || halo_live) && !(a.dbg_flags & 4)) {
+                const float4* src = X + (size_t)n0 * N + b0 + c;
+                float4* dst = lines + c * LP + (LINEAR ? ppos(n0) : 0);
+#pragma unroll
+                for (int k = 0; k < 16; ++k)  // row n0 + T k lands at position n0 + T ((k + 8) mod 16)
+                    mwfft::cp_async16(LINEAR ? dst + PRS * ((k + 8) & 15) : dst + spos(n0 + T * k), src + (size_t)(T * k) * N);
+            }
         }
+        mwfft::cp_async_wait_all();
+        MW_STAMP(1);
         __syncthreads();
-        if (!is_halo) {
+        MW_STAMP(2);
+        {
+            float4* line = lines + q * LP;
+            // the finished transform is (dx + i dz | sx + i sz): store it back as (dx, sx, dz, sz)
+            mwfft::fft_line<N, +1>(line, g, q, (!is_halo || halo_live) && !(a.dbg_flags & 2), tw2, tw3,
+                                   [&](int, int pidx, mwfft::cpk v) { line[pidx] = make_float4(v.re.x, v.re.y, v.im.x, v.im.y); });
+        }
+        MW_STAMP(3);
+        __syncthreads();
+        MW_STAMP(4);
+        if (!is_halo && !(a.dbg_flags & 16)) {
+            // thread <-> (row n0 + T k, column c), c fastest: a warp writes 8 rows x 4 columns per store
+            const int n0 = tid >> 2, c = tid & 3;
+            const float4* lp = lines + c * LP + (LINEAR ? ppos(n0) : 0);
+            const int dn = ppos(n0 + 1) - ppos(n0);  // padded distance to the next row (1 or 2)
+            const size_t o0 = obase + (size_t)n0 * N + b0 + c;
+            const bool last_col = b0 + c == N - 1;
 #pragma unroll 4
             for (int k = 0; k < 16; ++k) {
-                const int e = tid + k * MAIN;
-                const int ar = e >> LOGW, c = e & (W - 1);
-                const size_t o = obase + (size_t)ar * N + b0 + c;
-                const float2* pre = smem + 2 * c * PITCH;
-                const float2* pim = pre + PITCH;
-                const float2 vr = pre[pad_idx(ar)], vi = pim[pad_idx(ar)];  // (dx, sx), (dz, sz)
+                const int ar = n0 + RS * k;
+                size_t o = o0 + (size_t)(RS * k) * N;
+                if (a.dbg_flags & 16384) o = obase + (size_t)blockIdx.x * (4 * N) + k * (4 * T) + tid;  // experiment: contiguous stores
+                const float4* e = LINEAR ? lp + PRS * k : lp + ppos(ar);
+                const float4 v = e[0];  // (dx, sx, dz, sz)
                 // nor = normalize(up - n) = (sx, 1, sz) / |.|   (FFTMesh.cs:212, 218)
-                const float inv = rsqrtf(vr.y * vr.y + 1.0f + vi.y * vi.y);
-                const float nx = vr.y * inv, nz = vi.y * inv;
+                const float inv = rsqrtf(v.y * v.y + 1.0f + v.w * v.w);
+                const float nx = v.y * inv, nz = v.w * inv;
+                const bool st_ok = !(a.dbg_flags & 1) || inv == 123.0f;
                 if (a.normal) {
-                    a.normal[3 * o + 0] = nx;
-                    a.normal[3 * o + 1] = inv;
-                    a.normal[3 * o + 2] = nz;
+                    // the 4 lanes of a row hold 12 consecutive floats: regroup them into three 16-byte stores
+                    const float px = __shfl_down_sync(0xffffffffu, nx, 1), py = __shfl_down_sync(0xffffffffu, inv, 1),
+                                pz = __shfl_down_sync(0xffffffffu, nz, 1);
+                    float4* dst = reinterpret_cast<float4*>(a.normal + 3 * (o - c)) + c;
+                    if (a.dbg_flags & 16384) dst = reinterpret_cast<float4*>(a.normal + 3 * (o - tid)) + tid - (tid >> 2);
+                    if (st_ok) {
+                        if (c == 0) *dst = make_float4(nx, inv, nz, px);
+                        else if (c == 1) *dst = make_float4(inv, nz, px, py);
+                        else if (c == 2) *dst = make_float4(nz, px, py, pz);
+                    }
                 }
-                if (a.disp) a.disp[o] = make_float2(vr.x, vi.x);  // hds (FFTMesh.cs:247)
+                if (a.disp && st_ok) a.disp[o] = make_float2(v.x, v.z);  // hds (FFTMesh.cs:247)
                 if (want_white) {
                     float2 dDdx = make_float2(0.f, 0.f), dDdy = make_float2(0.f, 0.f);
                     if (ar != N - 1) {  // hds[index + resolution]  (:260-263)
-                        const float nbx = pre[pad_idx(ar + 1)].x, nbz = pim[pad_idx(ar + 1)].x;
-                        dDdx = make_float2(0.5f * (vr.x - nbx), 0.5f * (vi.x - nbz));
+                        const float4 nb = LINEAR ? e[dn] : lp[ppos(ar + 1)];
+                        dDdx = make_float2(0.5f * (v.x - nb.x), 0.5f * (v.z - nb.z));
                     }
-                    if (b0 + c != N - 1) {  // hds[index + 1]  (:264-267)
-                        const float nbx = pre[2 * PITCH + pad_idx(ar)].x, nbz = pim[2 * PITCH + pad_idx(ar)].x;
-                        dDdy = make_float2(0.5f * (vr.x - nbx), 0.5f * (vi.x - nbz));
+                    if (!last_col) {  // hds[index + 1]  (:264-267)
+                        const float4 nb = e[LP];
+                        dDdy = make_float2(0.5f * (v.x - nb.x), 0.5f * (v.z - nb.z));
                     }
                     const float jac = (1.0f + dDdx.x) * (1.0f + dDdy.y) - dDdx.y * dDdy.x;  // :268
-                    if (a.jacobian) a.jacobian[o] = jac;
-                    if (a.whitecap) {
+                    if (a.jacobian && st_ok) a.jacobian[o] = jac;
+                    if (a.whitecap && st_ok) {
                         // noise = |(|n.x|, |n.z|) * 0.3|   (:269-270)
                         const float ax = fabsf(nx) * 0.3f, az = fabsf(nz) * 0.3f;
                         float turb = fmaxf(1.0f - jac + sqrtf(ax * ax + az * az), 0.0f);  // :270
@@ -370,50 +414,45 @@ __global__ void __launch_bounds__((W + 1) * (N / 16), MINB) k_cols_extract(const
                 }
             }
         }
-        __syncthreads();
-    }
-
-    // ------------------------------------------------------------------ phase 2: C (height), W/2 packed lines
-    if (a.height) {
-        constexpr int HL = W / 2;       // packed lines
-        constexpr int HMAIN = HL * T;   // threads at work
+        MW_STAMP(5);
+    } else {
+        // ------------------------------------------------------------------ C slab: 8 columns = 4 packed lines
+        if (a.dbg_flags & 8) return;
+        const int b0 = ((int)blockIdx.x - a.ab_blocks) * 8;
         const float2* X = a.XC + obase;
-        const bool on = tid < HMAIN;
-        if (on) {
-            float4 v[16];  // (C[n][b].re, C[n][b].im, C[n][b+1].re, C[n][b+1].im)
+        const int n0 = tid >> 2, c2 = tid & 3;
+        if (!is_halo) {
+            // element (n, c2) = columns b0 + 2 c2, b0 + 2 c2 + 1 of row n: 16 contiguous bytes
+            // (re0, im0, re1, im1); the lanes are untangled to (re0, re1, im0, im1) after the first read
+            const float2* src = X + (size_t)n0 * N + b0 + 2 * c2;
+            float4* dst = lines + c2 * LP + (LINEAR ? ppos(n0) : 0);
 #pragma unroll
-            for (int k = 0; k < 16; ++k) {
-                const int e = tid + k * HMAIN;
-                const int n = e / HL, c2 = e % HL;
-                v[k] = __ldg(reinterpret_cast<const float4*>(X + (size_t)n * N + b0 + 2 * c2));
-            }
+            for (int k = 0; k < 16; ++k)
+                mwfft::cp_async16(LINEAR ? dst + PRS * ((k + 8) & 15) : dst + spos(n0 + RS * k), src + (size_t)(RS * k) * N);
+        }
+        mwfft::cp_async_wait_all();
+        __syncthreads();
+        float4* line = lines + q * LP;
+        if (!is_halo) {
+            float4* own = line + (LINEAR ? ppos(g) : 0);
 #pragma unroll
-            for (int k = 0; k < 16; ++k) {
-                const int e = tid + k * HMAIN;
-                const int n = e / HL, c2 = e % HL;
-                const int o = 2 * c2 * PITCH + pad_idx(n);
-                smem[o] = make_float2(v[k].x, v[k].z);
-                smem[o + PITCH] = make_float2(v[k].y, v[k].w);
+            for (int c = 0; c < 16; ++c) {  // own elements only: {g + T c}
+                float4* p = LINEAR ? own + PRS * c : own + ppos(g + T * c);
+                const float4 v = *p;
+                *p = make_float4(v.x, v.z, v.y, v.w);
             }
         }
+        // height = Re of the finished transform (FFTMesh.cs:219): lane x = column b, lane y = column b + 1
+        mwfft::fft_line<N, +1>(line, g, q, !is_halo, tw2, tw3,
+                               [&](int, int pidx, mwfft::cpk v) { *reinterpret_cast<float2*>(line + pidx) = v.re; });
         __syncthreads();
-        {
-            float2* pre = smem + 2 * q * PITCH;
-            float2* pim = pre + PITCH;
-            const int b = b0 + 2 * q;  // lane x = column b, lane y = column b + 1 (opposite sigma)
-            mwfft::fft_line<N, +1>(pre, pim, g, q, on, a.tw, [&](int idx, mwfft::cpk v) {
-                const float s = ((idx + b) & 1) ? 1.0f : -1.0f;
-                pre[pad_idx(idx)] = make_float2(s * v.re.x, -s * v.re.y);  // height = sigma * Re (FFTMesh.cs:219)
-            });
-        }
-        __syncthreads();
-        if (on) {
+        if (!is_halo) {
+            float* dst = a.height + obase + (size_t)n0 * N + b0 + 2 * c2;
+            const float4* lp = lines + c2 * LP + (LINEAR ? ppos(n0) : 0);
 #pragma unroll 4
             for (int k = 0; k < 16; ++k) {
-                const int e = tid + k * HMAIN;
-                const int n = e / HL, c2 = e % HL;
-                const float2 h = smem[2 * c2 * PITCH + pad_idx(n)];
-                *reinterpret_cast<float2*>(a.height + obase + (size_t)n * N + b0 + 2 * c2) = h;
+                const float2 h = *reinterpret_cast<const float2*>(LINEAR ? lp + PRS * k : lp + ppos(n0 + RS * k));
+                *reinterpret_cast<float2*>(dst + (size_t)(RS * k) * N) = h;
             }
         }
     }
