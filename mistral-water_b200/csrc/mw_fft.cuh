@@ -245,8 +245,8 @@ __device__ __forceinline__ void stage1(cpk (&v)[PTS], int g, Emit&& emit)
     emit_all<N, 16, 1>(v, g, emit);
 }
 // Stage 2 (radix R2, S = 16): twiddles W_{16 R2}^{r k}, k = j mod 16, one table row per butterfly
-template <int N, int SIGN, class Emit>
-__device__ __forceinline__ void stage2(cpk (&v)[PTS], int g, const float4* tw2, Emit&& emit)
+template <int N, int SIGN>
+__device__ __forceinline__ void stage2_compute(cpk (&v)[PTS], int g, const float4* tw2)
 {
     using P = Plan<N>;
     constexpr int R = P::R2, B = PTS / R, T = P::T;
@@ -262,11 +262,16 @@ __device__ __forceinline__ void stage2(cpk (&v)[PTS], int g, const float4* tw2, 
         }
     }
     dft_all<SIGN, R, B>(v);
-    emit_all<N, R, 16>(v, g, emit);
+}
+template <int N, int SIGN, class Emit>
+__device__ __forceinline__ void stage2(cpk (&v)[PTS], int g, const float4* tw2, Emit&& emit)
+{
+    stage2_compute<N, SIGN>(v, g, tw2);
+    emit_all<N, Plan<N>::R2, 16>(v, g, emit);
 }
 // Stage 3 (radix R3, S = 16 R2): twiddles W_N^{r k}; w^1 from the table, higher powers by multiplication
-template <int N, int SIGN, class Emit>
-__device__ __forceinline__ void stage3(cpk (&v)[PTS], int g, const float2* tw3, Emit&& emit)
+template <int N, int SIGN>
+__device__ __forceinline__ void stage3_compute(cpk (&v)[PTS], int g, const float2* tw3)
 {
     using P = Plan<N>;
     constexpr int R = P::R3, B = PTS / R, T = P::T, S = 16 * P::R2;
@@ -281,7 +286,12 @@ __device__ __forceinline__ void stage3(cpk (&v)[PTS], int g, const float2* tw3, 
         for (int r = 1; r < R; ++r) v[b + r * B] = pmul(v[b + r * B], pw[r].x, pw[r].y);
     }
     dft_all<SIGN, R, B>(v);
-    emit_all<N, R, S>(v, g, emit);
+}
+template <int N, int SIGN, class Emit>
+__device__ __forceinline__ void stage3(cpk (&v)[PTS], int g, const float2* tw3, Emit&& emit)
+{
+    stage3_compute<N, SIGN>(v, g, tw3);
+    emit_all<N, Plan<N>::R3, 16 * Plan<N>::R2>(v, g, emit);
 }
 
 template <int N>
@@ -339,6 +349,50 @@ __device__ __forceinline__ void fft_line(float4* line, int g, int line_id, bool 
         load_line_regs<N>(v, line, g);
         group_sync<T>(line_id);
         stage3<N, SIGN>(v, g, tw3, emit);
+    }
+}
+
+// Register-to-register variant for callers whose threads already hold their first-stage inputs
+// {line position g + T c} in v (loaded straight from global memory) and want the results left in
+// registers: on return slot s of v holds output index final_idx<N>(g, s).  `sync` must synchronise all
+// threads that share `line` (the caller chooses the thread <-> line mapping).  There is no "inactive"
+// path on purpose: a group without a real line transforms zeros in its own line buffer, so that every
+// thread of the CTA executes the same barrier instructions (no divergent __syncthreads).
+template <int N>
+struct Final {
+    using P = Plan<N>;
+    static constexpr int R = P::R3 == 1 ? P::R2 : P::R3;
+    static constexpr int S = P::R3 == 1 ? 16 : 16 * P::R2;
+    static constexpr int B = PTS / R;
+    static constexpr int NSYNC = P::R3 == 1 ? 2 : 4;
+};
+template <int N>
+__device__ __forceinline__ int final_idx(int g, int slot)
+{
+    using F = Final<N>;
+    const int b = slot % F::B, i = slot / F::B;
+    const int j = g + b * (N / PTS);
+    const int k = j & (F::S - 1);
+    return (j - k) * F::R + k + bitrev(i, ilog2(F::R)) * F::S;
+}
+template <int N, int SIGN, class Sync>
+__device__ __forceinline__ void fft_line_inreg(cpk (&v)[PTS], float4* line, int g, const float4* tw2, const float2* tw3,
+                                               Sync&& sync)
+{
+    using P = Plan<N>;
+    auto to_smem = [&](int, int pidx, cpk val) { line[pidx] = make_float4(val.re.x, val.re.y, val.im.x, val.im.y); };
+    stage1<N, SIGN>(v, g, to_smem);
+    sync();
+    load_line_regs<N>(v, line, g);
+    sync();  // everyone has read before anyone overwrites (in-place exchange)
+    if constexpr (P::R3 == 1) {
+        stage2_compute<N, SIGN>(v, g, tw2);
+    } else {
+        stage2<N, SIGN>(v, g, tw2, to_smem);
+        sync();
+        load_line_regs<N>(v, line, g);
+        sync();
+        stage3_compute<N, SIGN>(v, g, tw3);
     }
 }
 

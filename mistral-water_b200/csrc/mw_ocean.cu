@@ -1,5 +1,6 @@
 // mw_ocean.cu -- handle management and the C ABI of the ocean path (include/mistral_ocean.h).
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 #include <new>
 #include <vector>
@@ -45,12 +46,18 @@ struct mw_ocean {
     float2* ramp = nullptr;   // [2N]
     float* kd = nullptr;      // [N]
     float2* tw = nullptr;     // [N]
-    float4* XAB = nullptr;    // [tiles][N*N] intermediate, fields A and B (16 B / point)
-    float2* XC = nullptr;     // [tiles][N*N] intermediate, field C (8 B / point); lives right behind XAB
+    float4* XAB = nullptr;    // [tiles][N/4][N][5] intermediate, fields A and B + halo copies (20 B / point)
+    float2* XC = nullptr;     // [tiles][N/8][N][8] intermediate, field C (8 B / point); lives right behind XAB
     // scratch outputs (host-pointer mode, or inputs of k_mesh_outputs)
     float* s_height = nullptr; float2* s_disp = nullptr; float* s_normal = nullptr; float* s_white = nullptr;
     float* s_jac = nullptr; float* s_vert = nullptr; float4* s_col = nullptr; float2* s_h = nullptr;
     int dbg_flags = 0;
+    // tile-group pipelining: the frame is issued as groups of `group_tiles` tiles, alternating between two
+    // streams and two slots of the intermediate buffer, so that (a) the intermediate of a group stays in the
+    // 126 MB L2 between pass 1 and pass 2 and (b) pass 1 of one group overlaps pass 2 of the previous one
+    int group_tiles = 1, x_tiles = 1;
+    cudaStream_t aux_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     long long* dbg_rows = nullptr; long long* dbg_cols = nullptr;  // developer phase timing (mw_debug_phase_buffers)
     // profiling
     std::vector<EvPair> ev_pool; size_t ev_used = 0;
@@ -157,10 +164,22 @@ extern "C" int mw_ocean_create(const mw_ocean_params* params, mw_ocean** out)
     if ((rc = ensure(&o->kd, (size_t)N))) return fail(rc);
     if ((rc = ensure(&o->tw, (size_t)N))) return fail(rc);
     {
-        char* x = nullptr;  // one allocation: 24 B per grid point
-        if ((rc = ensure(&x, o->n2 * o->tiles * 24))) return fail(rc);
+        // group size: keep one group's intermediate (28 B per point) around 32 MB
+        long long gt = (32ll << 20) / (long long)(o->n2 * 28);
+        if (const char* e = getenv("MW_GROUP_TILES")) gt = atoll(e);
+        if (gt < 1) gt = 1;
+        if (gt > o->tiles) gt = o->tiles;
+        o->group_tiles = (int)gt;
+        o->x_tiles = o->tiles <= o->group_tiles ? o->tiles : 2 * o->group_tiles;
+        char* x = nullptr;  // one allocation: 28 B per grid point of x_tiles tiles
+        if ((rc = ensure(&x, o->n2 * o->x_tiles * 28))) return fail(rc);
         o->XAB = reinterpret_cast<float4*>(x);
-        o->XC = reinterpret_cast<float2*>(x + o->n2 * o->tiles * 16);
+        o->XC = reinterpret_cast<float2*>(x + o->n2 * o->x_tiles * 20);
+        if (cudaStreamCreateWithFlags(&o->aux_stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&o->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&o->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+            mw_set_error("stream/event creation failed"); return fail(MW_E_CUDA);
+        }
     }
 
     // small host-built tables
@@ -205,6 +224,9 @@ extern "C" void mw_ocean_destroy(mw_ocean* o)
     void* ptrs[] = {o->spec, o->omega, o->ramp, o->kd, o->tw, o->XAB, o->s_height, o->s_disp, o->s_normal,
                     o->s_white, o->s_jac, o->s_vert, o->s_col, o->s_h};
     for (void* q : ptrs) if (q) cudaFree(q);
+    if (o->aux_stream) { cudaStreamSynchronize(o->aux_stream); cudaStreamDestroy(o->aux_stream); }
+    if (o->ev_fork) cudaEventDestroy(o->ev_fork);
+    if (o->ev_join) cudaEventDestroy(o->ev_join);
     if (o->own_stream) cudaStreamDestroy(o->own_stream);
     delete o;
 }
@@ -250,15 +272,17 @@ extern "C" int mw_ocean_set_h0(mw_ocean* o, const float* h0, const float* h0conj
     if (!h0 || !h0conj) { mw_set_error("mw_ocean_set_h0: null buffer"); return MW_E_INVALID_ARG; }
     const size_t total = o->n2 * o->tiles;
     const float2 *d0 = (const float2*)h0, *d1 = (const float2*)h0conj;
+    float2* stage = nullptr;
     if (!o->device_ptrs) {
-        // stage through the intermediate buffer (24 B per point >= 2 float2), then interleave on the device
-        float2* stage = reinterpret_cast<float2*>(o->XAB);
+        // stage on the device, then interleave (h0, h0conj) into the packed spectrum
+        MW_CUDA(cudaMallocAsync((void**)&stage, 2 * total * sizeof(float2), o->stream));
         MW_CUDA(cudaMemcpyAsync(stage, h0, total * sizeof(float2), cudaMemcpyHostToDevice, o->stream));
         MW_CUDA(cudaMemcpyAsync(stage + total, h0conj, total * sizeof(float2), cudaMemcpyHostToDevice, o->stream));
         d0 = stage; d1 = stage + total;
     }
     mwk::k_pack_h0<<<(unsigned)((total + 255) / 256), 256, 0, o->stream>>>(o->spec, d0, d1, (int64_t)total);
     MW_LAUNCH_CHECK();
+    if (stage) MW_CUDA(cudaFreeAsync(stage, o->stream));
     if (!o->device_ptrs) MW_CUDA(cudaStreamSynchronize(o->stream));
     o->have_h0 = true;
     return MW_OK;
@@ -271,12 +295,17 @@ extern "C" int mw_ocean_get_h0(mw_ocean* o, float* h0, float* h0conj)
     if (!o->have_h0) { mw_set_error("h0 not initialised: call mw_ocean_init_spectrum or mw_ocean_set_h0 first"); return MW_E_STATE; }
     const size_t total = o->n2 * o->tiles;
     float2 *d0 = (float2*)h0, *d1 = (float2*)h0conj;
-    if (!o->device_ptrs) { d0 = reinterpret_cast<float2*>(o->XAB); d1 = d0 + total; }
+    float2* stage = nullptr;
+    if (!o->device_ptrs) {
+        MW_CUDA(cudaMallocAsync((void**)&stage, 2 * total * sizeof(float2), o->stream));
+        d0 = stage; d1 = stage + total;
+    }
     mwk::k_unpack_h0<<<(unsigned)((total + 255) / 256), 256, 0, o->stream>>>(o->spec, d0, d1, (int64_t)total);
     MW_LAUNCH_CHECK();
     if (!o->device_ptrs) {
         MW_CUDA(cudaMemcpyAsync(h0, d0, total * sizeof(float2), cudaMemcpyDeviceToHost, o->stream));
         MW_CUDA(cudaMemcpyAsync(h0conj, d1, total * sizeof(float2), cudaMemcpyDeviceToHost, o->stream));
+        MW_CUDA(cudaFreeAsync(stage, o->stream));
         MW_CUDA(cudaStreamSynchronize(o->stream));
     }
     return MW_OK;
@@ -330,7 +359,7 @@ extern "C" int mw_ocean_evolve_spectrum(mw_ocean* o, float t, float* htilde)
 // per-frame launches
 // ---------------------------------------------------------------------------------------------
 template <int N, int RP, int MINB>
-static int launch_rows(mw_ocean* o, const mwk::RowArgs& a)
+static int launch_rows(mw_ocean* o, const mwk::RowArgs& a, int ntiles, cudaStream_t st)
 {
     constexpr int threads = RP * 3 * (N / 16);
     constexpr size_t smem = mwfft::Plan<N>::TW_BYTES + (size_t)RP * 3 * mwfft::line_pitch(N, 8) * sizeof(float4);
@@ -341,15 +370,15 @@ static int launch_rows(mw_ocean* o, const mwk::RowArgs& a)
                                      cudaSharedmemCarveoutMaxShared));
         attr_done[o->p.device] = true;
     }
-    dim3 grid(N / 2 / RP, o->tiles);
+    dim3 grid(N / 2 / RP, ntiles);
     ProfScope ps(o, 0);
-    mwk::k_spectrum_rows<N, RP, MINB><<<grid, threads, smem, o->stream>>>(a);
+    mwk::k_spectrum_rows<N, RP, MINB><<<grid, threads, smem, st>>>(a);
     MW_LAUNCH_CHECK();
     return MW_OK;
 }
 
 template <int N, int MINB>
-static int launch_cols(mw_ocean* o, mwk::ColArgs a)
+static int launch_cols(mw_ocean* o, mwk::ColArgs a, int ntiles, cudaStream_t st)
 {
     constexpr int threads = 5 * (N / 16);
     constexpr size_t smem = mwfft::Plan<N>::TW_BYTES + (size_t)5 * mwfft::line_pitch(N, 4) * sizeof(float4);
@@ -364,29 +393,60 @@ static int launch_cols(mw_ocean* o, mwk::ColArgs a)
     a.ab_blocks = want_ab ? N / 4 : 0;
     const int c_blocks = a.height ? N / 8 : 0;
     if (a.ab_blocks + c_blocks == 0) return MW_OK;
-    dim3 grid(a.ab_blocks + c_blocks, o->tiles);
+    dim3 grid(a.ab_blocks + c_blocks, ntiles);
     ProfScope ps(o, 1);
-    mwk::k_cols_extract<N, MINB><<<grid, threads, smem, o->stream>>>(a);
+    mwk::k_cols_extract<N, MINB><<<grid, threads, smem, st>>>(a);
     MW_LAUNCH_CHECK();
+    return MW_OK;
+}
+
+template <int N, int RP, int RMINB, int CMINB>
+static int run_frame_n(mw_ocean* o, mwk::RowArgs ra, mwk::ColArgs ca)
+{
+    int rc;
+    const int G = o->group_tiles;
+    const int ngroups = (o->tiles + G - 1) / G;
+    // MW_PROFILE handles stay on one stream so that the per-kernel event times are not overlapped
+    const bool dual = ngroups > 1 && !o->profile;
+    if (dual) {
+        MW_CUDA(cudaEventRecord(o->ev_fork, o->stream));
+        MW_CUDA(cudaStreamWaitEvent(o->aux_stream, o->ev_fork, 0));
+    }
+    float4* xab0 = o->XAB;
+    float2* xc0 = o->XC;
+    for (int gi = 0; gi < ngroups; ++gi) {
+        const int t0 = gi * G;
+        const int nt = o->tiles - t0 < G ? o->tiles - t0 : G;
+        const int slot = ngroups > 1 ? (gi & 1) : 0;
+        cudaStream_t st = (dual && (gi & 1)) ? o->aux_stream : o->stream;
+        ra.tile0 = ca.tile0 = t0;
+        ra.XAB = xab0 + (size_t)slot * G * o->n2 * 5 / 4;
+        ra.XC = xc0 + (size_t)slot * G * o->n2;
+        ca.XAB = ra.XAB;
+        ca.XC = ra.XC;
+        if ((rc = launch_rows<N, RP, RMINB>(o, ra, nt, st))) return rc;
+        if ((rc = launch_cols<N, CMINB>(o, ca, nt, st))) return rc;
+    }
+    if (dual) {
+        MW_CUDA(cudaEventRecord(o->ev_join, o->aux_stream));
+        MW_CUDA(cudaStreamWaitEvent(o->stream, o->ev_join, 0));
+    }
     return MW_OK;
 }
 
 static int run_frame(mw_ocean* o, const mwk::RowArgs& ra, const mwk::ColArgs& ca)
 {
-    int rc;
     switch (o->N) {
-#define MW_CASE(N_, RP_, RMINB_, CMINB_)                                      \
-    case N_:                                                                  \
-        if ((rc = launch_rows<N_, RP_, RMINB_>(o, ra))) return rc;            \
-        return launch_cols<N_, CMINB_>(o, ca);
-        MW_CASE(32, 16, 1, 1)
-        MW_CASE(64, 8, 1, 1)
-        MW_CASE(128, 8, 1, 1)
-        MW_CASE(256, 4, 2, 2)
-        MW_CASE(512, 2, 2, 2)
-        MW_CASE(1024, 1, 3, 2)
-        MW_CASE(2048, 1, 1, 1)
-#undef MW_CASE
+        case 32: return run_frame_n<32, 16, 1, 1>(o, ra, ca);
+        case 64: return run_frame_n<64, 8, 1, 1>(o, ra, ca);
+        case 128: return run_frame_n<128, 8, 1, 1>(o, ra, ca);
+        case 256: return run_frame_n<256, 4, 2, 2>(o, ra, ca);
+        case 512: return run_frame_n<512, 2, 2, 2>(o, ra, ca);
+        case 1024: {
+            static const int minb = getenv("MW_ROWS_MINB") ? atoi(getenv("MW_ROWS_MINB")) : 3;
+            return minb == 3 ? run_frame_n<1024, 1, 3, 2>(o, ra, ca) : run_frame_n<1024, 1, 4, 2>(o, ra, ca);
+        }
+        case 2048: return run_frame_n<2048, 1, 1, 1>(o, ra, ca);
     }
     mw_set_error("unsupported resolution %d", o->N);
     return MW_E_INVALID_ARG;
@@ -425,8 +485,8 @@ extern "C" int mw_ocean_generate(mw_ocean* o, float t, const mw_ocean_out* out)
         else { if ((rc = ensure(&o->s_jac, total))) return rc; d_jac = o->s_jac; }
     }
 
-    mwk::RowArgs ra{o->spec, o->omega, o->ramp, o->kd, o->tw, o->XAB, o->XC, t, o->dbg_rows, o->dbg_flags};
-    mwk::ColArgs ca{o->XAB, o->XC, o->tw, d_height, d_disp, d_normal, d_white, d_jac, o->dbg_cols, o->dbg_flags, 0};
+    mwk::RowArgs ra{o->spec, o->omega, o->ramp, o->kd, o->tw, o->XAB, o->XC, t, 0, o->dbg_rows, o->dbg_flags};
+    mwk::ColArgs ca{o->XAB, o->XC, o->tw, d_height, d_disp, d_normal, d_white, d_jac, o->dbg_cols, o->dbg_flags, 0, 0};
     if ((rc = run_frame(o, ra, ca))) return rc;
 
     float* d_vert = nullptr; float4* d_col = nullptr;

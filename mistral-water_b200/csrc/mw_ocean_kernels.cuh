@@ -139,18 +139,26 @@ __global__ void k_evolve(const float4* __restrict__ spec, const float* __restric
 // =============================================================================================
 // pass 1: evolve + pack + row FFT
 // =============================================================================================
-// Intermediate layout (ours to choose; 24 B per grid point):
-//   XAB[tile][n][b] : float4 (A.re, B.re, A.im, B.im)   A = chop-displacement field, B = slope field
-//   XC [tile][n][b] : float2 (C.re, C.im)               C = height field
+// Intermediate layout (ours to choose), SLAB-MAJOR so that what one pass-2 CTA reads is one contiguous
+// block of memory (a row-major intermediate makes pass 2 read 64-byte pieces 16 KB apart, which runs the
+// HBM at a fraction of its bandwidth -- measured):
+//   XAB[tile][b / 4][n][5] : float4 (A.re, B.re, A.im, B.im), A = chop-displacement field, B = slope field;
+//                            entries 0..3 = columns 4s..4s+3 of row n, entry 4 = a copy of column 4s+4
+//                            (the halo the Jacobian's forward difference needs)        20 B per grid point
+//   XC [tile][b / 8][n][8] : float2 (C.re, C.im), C = height field                       8 B per grid point
+// Pass 1 therefore scatters 64-byte pieces (writes: they are merged in the 126 MB L2 before they reach HBM).
+__host__ __device__ constexpr size_t xab_index(int N, int n, int b) { return ((size_t)(b >> 2) * N + n) * 5 + (b & 3); }
+__host__ __device__ constexpr size_t xc_index(int N, int n, int b) { return ((size_t)(b >> 3) * N + n) * 8 + (b & 7); }
 struct RowArgs {
     const float4* spec;    // [tiles][N][N]  (h0, h0conj)
     const float* omega;    // [N][N]
     const float2* ramp;    // [2N]  exp(i pi s (1-N)/N), s = n + m
     const float* kd;       // [N]   2 pi (i - N/2) / L, fp32 as FFTMesh.cs:201
     const float2* tw;      // [N]   exp(+2 pi i x / N)
-    float4* XAB;           // [tiles][N][N]
-    float2* XC;            // [tiles][N][N]
+    float4* XAB;           // [tiles][N/4][N][5]
+    float2* XC;            // [tiles][N/8][N][8]
     float t;
+    int tile0;             // first tile of this launch (blockIdx.y counts from it); X is indexed by blockIdx.y
     long long* dbg;        // developer phase-timing buffer (NULL in production)
     int dbg_flags;         // developer experiments: 1 = no output stores, 2 = no FFT, 4 = no spectrum loads
 };
@@ -185,7 +193,8 @@ __global__ void __launch_bounds__(RP * 3 * (N / 16), MINB) k_spectrum_rows(const
     float2* tw3 = reinterpret_cast<float2*>(smem4 + P::TW2_F4);
     float4* all_lines = smem4 + P::TW_BYTES / 16;
 
-    const int tile = blockIdx.y;
+    const int tile = a.tile0 + blockIdx.y;  // spectrum / global tile index
+    const int xt = blockIdx.y;              // slot inside the intermediate buffer of this launch
     const int rp = threadIdx.x / PAIR_THREADS;
     const int lt = threadIdx.x % PAIR_THREADS;
     const int pair = blockIdx.x * RP + rp;  // < N/2
@@ -204,6 +213,7 @@ __global__ void __launch_bounds__(RP * 3 * (N / 16), MINB) k_spectrum_rows(const
     // ---- evolve + pack.  One task = the four grid points (rA|rB, m|m') with m' = -m mod N; the set is
     //      closed under k -> -k, so every Hermitian partner is on hand and every point is read once. ----
     if (a.dbg_flags & 512) return;
+#pragma unroll 1
     for (int m = lt; m <= N / 2 && !(a.dbg_flags & 32); m += PAIR_THREADS) {
         const int mm = (N - m) & (N - 1);
         const float4 s1 = ldg_stream4(spec + rA * N + m);    // P1 = (rA, m)
@@ -259,19 +269,36 @@ __global__ void __launch_bounds__(RP * 3 * (N / 16), MINB) k_spectrum_rows(const
     // ---- row FFT of the three packed lines ----
     const int q = lt / T, g = lt % T;
     float4* line = lines + q * LP;
-    const size_t tbase = (size_t)tile * N * N;
     if (a.dbg_flags & 64) return;
-    if (q < 2) {
-        float4* dst = a.XAB + tbase + (size_t)(q ? rB : rA) * N;
-        mwfft::fft_line<N, +1>(line, g, rp * 3 + q, true, tw2, tw3,
-                               [&](int idx, int, mwfft::cpk v) { dst[idx] = make_float4(v.re.x, v.re.y, v.im.x, v.im.y); });
-    } else {
-        float2* dA = a.XC + tbase + (size_t)rA * N;
-        float2* dB = a.XC + tbase + (size_t)rB * N;
-        mwfft::fft_line<N, +1>(line, g, rp * 3 + q, true, tw2, tw3, [&](int idx, int, mwfft::cpk v) {
-            dA[idx] = make_float2(v.re.x, v.im.x);
-            dB[idx] = make_float2(v.re.y, v.im.y);
-        });
+    {
+        // one instance of the transform for all three lines (code size: the kernel has to stay resident in
+        // the instruction cache while several CTAs run different phases); results come back in registers
+        mwfft::cpk v[16];
+        mwfft::load_line_regs<N>(v, line, g);
+        const int bar_id = rp * 3 + q;
+        auto line_sync = [&] { mwfft::group_sync<T>(bar_id); };
+        line_sync();  // everyone has read before anyone overwrites (in-place exchange)
+        mwfft::fft_line_inreg<N, +1>(v, line, g, tw2, tw3, line_sync);
+        if (q < 2) {
+            const int row = q ? rB : rA;
+            float4* dst = a.XAB + (size_t)xt * N * N * 5 / 4;
+#pragma unroll
+            for (int sl = 0; sl < 16; ++sl) {
+                const int idx = mwfft::final_idx<N>(g, sl);
+                const float4 e = make_float4(v[sl].re.x, v[sl].re.y, v[sl].im.x, v[sl].im.y);
+                const size_t at = xab_index(N, row, idx);
+                dst[at] = e;
+                if ((idx & 3) == 0 && idx != 0) dst[at - (size_t)N * 5 + 4] = e;  // halo copy for the slab to the west
+            }
+        } else {
+            float2* dst = a.XC + (size_t)xt * N * N;
+#pragma unroll
+            for (int sl = 0; sl < 16; ++sl) {
+                const int idx = mwfft::final_idx<N>(g, sl);
+                dst[xc_index(N, rA, idx)] = make_float2(v[sl].re.x, v[sl].im.x);
+                dst[xc_index(N, rB, idx)] = make_float2(v[sl].re.y, v[sl].im.y);
+            }
+        }
     }
     MW_RSTAMP(3);
 }
@@ -280,8 +307,8 @@ __global__ void __launch_bounds__(RP * 3 * (N / 16), MINB) k_spectrum_rows(const
 // pass 2: column FFT + extraction (+ Jacobian whitecap)
 // =============================================================================================
 struct ColArgs {
-    const float4* XAB;  // [tiles][N][N]
-    const float2* XC;   // [tiles][N][N]
+    const float4* XAB;  // [tiles][N/4][N][5]
+    const float2* XC;   // [tiles][N/8][N][8]
     const float2* tw;   // [N]
     float* height;      // [tiles][N*N]     or NULL
     float2* disp;       // [tiles][N*N]     or NULL   (hds)
@@ -290,172 +317,168 @@ struct ColArgs {
     float* jacobian;    // [tiles][N*N]     or NULL
     long long* dbg;     // developer phase-timing buffer (NULL in production): 8 clock64 stamps per CTA
     int dbg_flags;      // developer experiments (tools/phase_timing.py)
+    int tile0;          // first tile of this launch (outputs are indexed by tile0 + blockIdx.y, X by blockIdx.y)
     int ab_blocks;      // blockIdx.x <  ab_blocks : (A,B) slab of 4 columns  (0 if no A/B output is wanted)
                         // blockIdx.x >= ab_blocks : C slab of 8 columns
 };
 
-// 5 packed-line thread groups per CTA, two kinds of CTA in one launch:
+// 5 packed lines per CTA, two kinds of CTA in one launch:
 //   (A,B) CTA: the (A,B) pairs of 4 columns + the halo column b0 + 4 (so that hds[index + 1] of
 //              FFTMesh.cs:266 is on chip)  -> hds, normal, Jacobian, whitecap
-//   C CTA    : the C field of 8 columns, two columns per packed line (4 groups busy)  -> height
-// The slab goes global -> shared with 16-byte cp.async straight into its transposed place (the element
-// formats of XAB and of the packed line are the same 16 bytes), so the load costs no registers.
+//   C CTA    : the C field of 8 columns, two columns per packed line (4 lines busy)  -> height
+//
+// Thread <-> data: thread tid < 4T owns line c = tid & 3 and residue g = tid >> 2 of the line (T = N/16
+// residues), so a warp is 8 consecutive g x 4 columns.  With that mapping
+//   * the first-stage inputs {row g + T k} x {4 columns} are loaded from global memory straight into
+//     registers as 64-byte row segments (no staging copy, no transposition pass);
+//   * after the last stage a warp holds 8 consecutive rows x 4 columns of finished values in
+//     registers, which is exactly the shape of a coalesced store: normals, hds and the whitecap are
+//     computed from registers; only the (dx, dz) pairs go through shared memory once more, for the
+//     forward differences of the Jacobian (FFTMesh.cs:260-267).
+// Threads tid >= 4T (one more group of T) run the halo line.
 template <int N, int MINB>
 __global__ void __launch_bounds__(5 * (N / 16), MINB) k_cols_extract(const ColArgs a)
 {
     using P = Plan<N>;
+    using F = mwfft::Final<N>;
     constexpr int T = P::T;
     constexpr int W = 4;
     constexpr int LP = mwfft::line_pitch(N, W);
-    constexpr int RS = 4 * T / W;                   // row step of the 4-column thread mapping (= T)
-    constexpr int PRS = mwfft::pad_step(RS);        // ... in padded line positions (T % 16 == 0 for N >= 256)
     constexpr bool LINEAR = (T % 16 == 0);
     extern __shared__ float4 smem4[];
     float4* tw2 = smem4;
     float2* tw3 = reinterpret_cast<float2*>(smem4 + P::TW2_F4);
     float4* lines = smem4 + P::TW_BYTES / 16;  // [5][LP]
 
-    const int tile = blockIdx.y;
+    const int tile = a.tile0 + blockIdx.y;
+    const int xt = blockIdx.y;
     const int tid = threadIdx.x;
-    const int q = tid / T, g = tid % T;
-    const bool is_halo = q == W;
+    const bool is_halo = tid >= W * T;
+    const int c = is_halo ? W : (tid & 3);
+    const int g = is_halo ? tid - W * T : (tid >> 2);
     const size_t plane = (size_t)N * N;
     const size_t obase = (size_t)tile * plane;
-    // padded position of row n, and of row (n + N/2) mod N where the loads put it (the (-1)^a of sigma)
-    auto ppos = [](int n) { return pad_idx(n); };
-    auto spos = [](int n) { return pad_idx((n + N / 2) & (N - 1)); };
+    float4* line = lines + c * LP;
+    auto cta_sync = [] { __syncthreads(); };
 
     mwfft::load_twiddles<N, +1>(tw2, tw3, a.tw);
 #define MW_STAMP(i) do { if (a.dbg && tid == 0) a.dbg[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 8 + (i)] = clock64(); } while (0)
     MW_STAMP(0);
-    if (a.dbg_flags & 256) return;
+    __syncthreads();  // twiddle tables visible
 
-    if ((int)blockIdx.x < a.ab_blocks) {
-        // ------------------------------------------------------------------ (A, B) slab
-        const int b0 = blockIdx.x * W;
-        const bool want_white = a.whitecap != nullptr || a.jacobian != nullptr;
-        const bool halo_live = want_white && b0 + W < N;
-        const float4* X = a.XAB + obase;
-        {
-            // all 5 T threads: thread <-> (row n0 = tid / 5 + T k, column c = tid % 5); a row's 5 elements
-            // (4 slab columns + the halo column) are 80 contiguous bytes
-            const int n0 = tid / 5, c = tid - 5 * n0;
-            if ((c < W || halo_live) && !(a.dbg_flags & 4)) {
-                const float4* src = X + (size_t)n0 * N + b0 + c;
-                float4* dst = lines + c * LP + (LINEAR ? ppos(n0) : 0);
+    mwfft::cpk v[16];
+    const bool is_ab = (int)blockIdx.x < a.ab_blocks;
+    const bool want_white = a.whitecap != nullptr || a.jacobian != nullptr;
+    const int b0 = is_ab ? blockIdx.x * W : ((int)blockIdx.x - a.ab_blocks) * 8;
+    // a group without a live line (halo group of a C slab, of the last slab, or when no whitecap is wanted)
+    // transforms zeros: same instruction stream for every thread, no divergent barrier
+    const bool active = is_ab ? (!is_halo || (want_white && b0 + W < N)) : !is_halo;
+    if ((a.dbg_flags & 8) && !is_ab) return;
+
+    // ---- first-stage inputs straight from global memory: line position p = g + T k holds intermediate row
+    //      (p + N/2) mod N = g + T ((k + 8) mod 16)  (the (-1)^a of sigma); slab-major layout => contiguous ----
+    if (is_ab) {
+        const float4* src = a.XAB + (size_t)xt * plane * 5 / 4 + ((size_t)blockIdx.x * N + g) * 5 + c;
 #pragma unroll
-                for (int k = 0; k < 16; ++k)  // row n0 + T k lands at position n0 + T ((k + 8) mod 16)
-                    mwfft::cp_async16(LINEAR ? dst + PRS * ((k + 8) & 15) : dst + spos(n0 + T * k), src + (size_t)(T * k) * N);
-            }
+        for (int k = 0; k < 16; ++k) {
+            float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (active && !(a.dbg_flags & 4)) e = ldg_stream4(src + (size_t)(T * ((k + 8) & 15)) * 5);
+            v[k].re = make_float2(e.x, e.y);
+            v[k].im = make_float2(e.z, e.w);
         }
-        mwfft::cp_async_wait_all();
-        MW_STAMP(1);
-        __syncthreads();
-        MW_STAMP(2);
-        {
-            float4* line = lines + q * LP;
-            // the finished transform is (dx + i dz | sx + i sz): store it back as (dx, sx, dz, sz)
-            mwfft::fft_line<N, +1>(line, g, q, (!is_halo || halo_live) && !(a.dbg_flags & 2), tw2, tw3,
-                                   [&](int, int pidx, mwfft::cpk v) { line[pidx] = make_float4(v.re.x, v.re.y, v.im.x, v.im.y); });
-        }
-        MW_STAMP(3);
-        __syncthreads();
-        MW_STAMP(4);
-        if (!is_halo && !(a.dbg_flags & 16)) {
-            // thread <-> (row n0 + T k, column c), c fastest: a warp writes 8 rows x 4 columns per store
-            const int n0 = tid >> 2, c = tid & 3;
-            const float4* lp = lines + c * LP + (LINEAR ? ppos(n0) : 0);
-            const int dn = ppos(n0 + 1) - ppos(n0);  // padded distance to the next row (1 or 2)
-            const size_t o0 = obase + (size_t)n0 * N + b0 + c;
-            const bool last_col = b0 + c == N - 1;
-#pragma unroll 4
-            for (int k = 0; k < 16; ++k) {
-                const int ar = n0 + RS * k;
-                size_t o = o0 + (size_t)(RS * k) * N;
-                if (a.dbg_flags & 16384) o = obase + (size_t)blockIdx.x * (4 * N) + k * (4 * T) + tid;  // experiment: contiguous stores
-                const float4* e = LINEAR ? lp + PRS * k : lp + ppos(ar);
-                const float4 v = e[0];  // (dx, sx, dz, sz)
-                // nor = normalize(up - n) = (sx, 1, sz) / |.|   (FFTMesh.cs:212, 218)
-                const float inv = rsqrtf(v.y * v.y + 1.0f + v.w * v.w);
-                const float nx = v.y * inv, nz = v.w * inv;
-                const bool st_ok = !(a.dbg_flags & 1) || inv == 123.0f;
-                if (a.normal) {
-                    // the 4 lanes of a row hold 12 consecutive floats: regroup them into three 16-byte stores
-                    const float px = __shfl_down_sync(0xffffffffu, nx, 1), py = __shfl_down_sync(0xffffffffu, inv, 1),
-                                pz = __shfl_down_sync(0xffffffffu, nz, 1);
-                    float4* dst = reinterpret_cast<float4*>(a.normal + 3 * (o - c)) + c;
-                    if (a.dbg_flags & 16384) dst = reinterpret_cast<float4*>(a.normal + 3 * (o - tid)) + tid - (tid >> 2);
-                    if (st_ok) {
-                        if (c == 0) *dst = make_float4(nx, inv, nz, px);
-                        else if (c == 1) *dst = make_float4(inv, nz, px, py);
-                        else if (c == 2) *dst = make_float4(nz, px, py, pz);
-                    }
-                }
-                if (a.disp && st_ok) a.disp[o] = make_float2(v.x, v.z);  // hds (FFTMesh.cs:247)
-                if (want_white) {
-                    float2 dDdx = make_float2(0.f, 0.f), dDdy = make_float2(0.f, 0.f);
-                    if (ar != N - 1) {  // hds[index + resolution]  (:260-263)
-                        const float4 nb = LINEAR ? e[dn] : lp[ppos(ar + 1)];
-                        dDdx = make_float2(0.5f * (v.x - nb.x), 0.5f * (v.z - nb.z));
-                    }
-                    if (!last_col) {  // hds[index + 1]  (:264-267)
-                        const float4 nb = e[LP];
-                        dDdy = make_float2(0.5f * (v.x - nb.x), 0.5f * (v.z - nb.z));
-                    }
-                    const float jac = (1.0f + dDdx.x) * (1.0f + dDdy.y) - dDdx.y * dDdy.x;  // :268
-                    if (a.jacobian && st_ok) a.jacobian[o] = jac;
-                    if (a.whitecap && st_ok) {
-                        // noise = |(|n.x|, |n.z|) * 0.3|   (:269-270)
-                        const float ax = fabsf(nx) * 0.3f, az = fabsf(nz) * 0.3f;
-                        float turb = fmaxf(1.0f - jac + sqrtf(ax * ax + az * az), 0.0f);  // :270
-                        turb = fminf(turb, 1.0f);                                          // SmoothStep clamps
-                        a.whitecap[o] = -2.0f * turb * turb * turb + 3.0f * turb * turb;   // :273
-                    }
-                }
-            }
-        }
-        MW_STAMP(5);
     } else {
-        // ------------------------------------------------------------------ C slab: 8 columns = 4 packed lines
-        if (a.dbg_flags & 8) return;
-        const int b0 = ((int)blockIdx.x - a.ab_blocks) * 8;
-        const float2* X = a.XC + obase;
-        const int n0 = tid >> 2, c2 = tid & 3;
-        if (!is_halo) {
-            // element (n, c2) = columns b0 + 2 c2, b0 + 2 c2 + 1 of row n: 16 contiguous bytes
-            // (re0, im0, re1, im1); the lanes are untangled to (re0, re1, im0, im1) after the first read
-            const float2* src = X + (size_t)n0 * N + b0 + 2 * c2;
-            float4* dst = lines + c2 * LP + (LINEAR ? ppos(n0) : 0);
+        // 16 contiguous bytes = columns b0 + 2c, b0 + 2c + 1 of one row: (re0, im0, re1, im1)
+        const float4* src = reinterpret_cast<const float4*>(a.XC + (size_t)xt * plane + ((size_t)(b0 >> 3) * N + g) * 8 + (active ? 2 * c : 0));
 #pragma unroll
-            for (int k = 0; k < 16; ++k)
-                mwfft::cp_async16(LINEAR ? dst + PRS * ((k + 8) & 15) : dst + spos(n0 + RS * k), src + (size_t)(RS * k) * N);
+        for (int k = 0; k < 16; ++k) {
+            float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (active) e = ldg_stream4(src + (size_t)(T * ((k + 8) & 15)) * 4);
+            v[k].re = make_float2(e.x, e.z);
+            v[k].im = make_float2(e.y, e.w);
         }
-        mwfft::cp_async_wait_all();
-        __syncthreads();
-        float4* line = lines + q * LP;
-        if (!is_halo) {
-            float4* own = line + (LINEAR ? ppos(g) : 0);
+    }
+    MW_STAMP(1);
+    if (!(a.dbg_flags & 2)) mwfft::fft_line_inreg<N, +1>(v, line, g, tw2, tw3, cta_sync);  // one instance for both kinds
+    MW_STAMP(2);
+
+    if (!is_ab) {
+        if (active) {
+            // height = Re of the finished transform (FFTMesh.cs:219); lane x = column b, lane y = column b + 1
+            float* dst = a.height + obase + (size_t)g * N + b0 + 2 * c;
 #pragma unroll
-            for (int c = 0; c < 16; ++c) {  // own elements only: {g + T c}
-                float4* p = LINEAR ? own + PRS * c : own + ppos(g + T * c);
-                const float4 v = *p;
-                *p = make_float4(v.x, v.z, v.y, v.w);
+            for (int s = 0; s < 16; ++s) {
+                const int ar = mwfft::final_idx<N>(g, s);
+                *reinterpret_cast<float2*>(dst + (size_t)(ar - g) * N) = v[s].re;
             }
         }
-        // height = Re of the finished transform (FFTMesh.cs:219): lane x = column b, lane y = column b + 1
-        mwfft::fft_line<N, +1>(line, g, q, !is_halo, tw2, tw3,
-                               [&](int, int pidx, mwfft::cpk v) { *reinterpret_cast<float2*>(line + pidx) = v.re; });
-        __syncthreads();
-        if (!is_halo) {
-            float* dst = a.height + obase + (size_t)n0 * N + b0 + 2 * c2;
-            const float4* lp = lines + c2 * LP + (LINEAR ? ppos(n0) : 0);
-#pragma unroll 4
-            for (int k = 0; k < 16; ++k) {
-                const float2 h = *reinterpret_cast<const float2*>(LINEAR ? lp + PRS * k : lp + ppos(n0 + RS * k));
-                *reinterpret_cast<float2*>(dst + (size_t)(RS * k) * N) = h;
+        return;
+    }
+
+    // ------------------------------------------------------------------ (A, B) slab
+    // finished transform: lane x = dx + i dz, lane y = sx + i sz.  (dx, dz) to shared memory (in place of the
+    // line, 8 bytes per row) for the neighbours' forward differences.
+    float2* D = reinterpret_cast<float2*>(line);
+    const int pg = pad_idx(g);
+    if (want_white) {
+#pragma unroll
+        for (int s = 0; s < 16; ++s) {
+            const int ar = mwfft::final_idx<N>(g, s);
+            D[LINEAR ? pg + mwfft::pad_step(ar - g) : pad_idx(ar)] = make_float2(v[s].re.x, v[s].im.x);
+        }
+    }
+    __syncthreads();
+    MW_STAMP(3);
+    {
+        const bool own = !is_halo && !(a.dbg_flags & 1);  // halo threads run the same code with every memory access predicated off
+        if (a.dbg_flags & 16) return;
+        const int dn = pad_idx(g + 1) - pg;  // padded distance to the next row (1 or 2)
+        const size_t o0 = obase + (size_t)g * N + b0 + c;
+        const bool last_col = b0 + c == N - 1;
+        const float2* De = reinterpret_cast<const float2*>(line + LP);  // east neighbour's line
+#pragma unroll
+        for (int s = 0; s < 16; ++s) {
+            const int ar = mwfft::final_idx<N>(g, s);
+            const size_t o = o0 + (size_t)(ar - g) * N;
+            const float dx = v[s].re.x, sx = v[s].re.y, dz = v[s].im.x, sz = v[s].im.y;
+            // nor = normalize(up - n) = (sx, 1, sz) / |.|   (FFTMesh.cs:212, 218)
+            const float inv = rsqrtf(sx * sx + 1.0f + sz * sz);
+            const float nx = sx * inv, nz = sz * inv;
+            if (a.normal) {
+                // the 4 lanes of a row hold 12 consecutive floats: regroup them into three 16-byte stores
+                // (shuffles are executed by every lane of the warp, stores only by owners)
+                const float px = __shfl_down_sync(0xffffffffu, nx, 1), py = __shfl_down_sync(0xffffffffu, inv, 1),
+                            pz = __shfl_down_sync(0xffffffffu, nz, 1);
+                float4* dst = reinterpret_cast<float4*>(a.normal + 3 * (o - c)) + c;
+                if (own && c == 0) *dst = make_float4(nx, inv, nz, px);
+                else if (own && c == 1) *dst = make_float4(inv, nz, px, py);
+                else if (own && c == 2) *dst = make_float4(nz, px, py, pz);
+            }
+            if (a.disp && own) a.disp[o] = make_float2(dx, dz);  // hds (FFTMesh.cs:247)
+            if (want_white && own) {
+                const int pa = LINEAR ? pg + mwfft::pad_step(ar - g) : pad_idx(ar);
+                float2 dDdx = make_float2(0.f, 0.f), dDdy = make_float2(0.f, 0.f);
+                if (ar != N - 1) {  // hds[index + resolution]  (:260-263)
+                    const float2 nb = D[LINEAR ? pa + dn : pad_idx(ar + 1)];
+                    dDdx = make_float2(0.5f * (dx - nb.x), 0.5f * (dz - nb.y));
+                }
+                if (!last_col) {  // hds[index + 1]  (:264-267)
+                    const float2 nb = De[pa];
+                    dDdy = make_float2(0.5f * (dx - nb.x), 0.5f * (dz - nb.y));
+                }
+                const float jac = (1.0f + dDdx.x) * (1.0f + dDdy.y) - dDdx.y * dDdy.x;  // :268
+                if (a.jacobian) a.jacobian[o] = jac;
+                if (a.whitecap) {
+                    // noise = |(|n.x|, |n.z|) * 0.3|   (:269-270)
+                    const float ax = fabsf(nx) * 0.3f, az = fabsf(nz) * 0.3f;
+                    float turb = fmaxf(1.0f - jac + sqrtf(ax * ax + az * az), 0.0f);  // :270
+                    turb = fminf(turb, 1.0f);                                          // SmoothStep clamps
+                    a.whitecap[o] = -2.0f * turb * turb * turb + 3.0f * turb * turb;   // :273
+                }
             }
         }
     }
+    MW_STAMP(4);
+    (void)F::R;
 }
 
 // =============================================================================================

@@ -27,19 +27,7 @@ def timeit(flags, K=20):
         for i in range(K): o.generate(0.1 * i, bufs)
         ms, n = o.kernel_times()
     return ms[0] / n[0] * 1e3, ms[1] / n[1] * 1e3
-for fl, name in ((16384, "AB: contiguous (wrong-place) stores"), (16384 + 8, "same, no C"),
-                 (0, "full"), (1, "AB: no output stores"), (2, "AB: no FFT"), (4, "AB: no slab load"), (7, "AB: only extract math"), (7 + 16, "AB: nothing, C full"), (8, "no C"), (8 + 7 + 16, "cols: only twiddle load + barriers"), (256, "cols: return at once"),
-                 (32, "rows: no evolve"), (64, "rows: no fft/store"), (32 + 64, "rows: only twiddles"), (512, "rows: return before evolve")):
+for fl, name in ((0, "full"), (1, "AB: no stores"), (16, "AB: no extraction"), (2, "AB: no FFT"), (4, "AB: no loads"), (8, "no C"), (8 + 16, "no C, no extraction"), (8 + 16 + 2, "no C, only loads"), (8+16+2+4, "nothing"),
+                 (32, "rows: no evolve"), (64, "rows: no fft/store")):
     r, c = timeit(fl)
     print(f"flags={fl:4d} ({name:36s}): rows {r:6.0f} us   cols {c:6.0f} us   per 16-tile frame")
-lib.mw_debug_flags(o._h, 0)
-with torch.cuda.stream(st):
-    lib.mw_debug_phase_buffers(o._h, dr.data_ptr(), dc.data_ptr())
-    o.generate(0.5, bufs); torch.cuda.synchronize()
-r = dr.cpu().numpy().reshape(-1, 8); c = dc.cpu().numpy().reshape(tiles, -1, 8)
-d = np.diff(r[:, :4], axis=1)
-print("rows kernel, cycles per CTA: evolve %.0f  sync %.0f  fft+store %.0f   total %.0f" % (*d.mean(0), (r[:, 3] - r[:, 0]).mean()))
-ab = c[:, : N // 4].reshape(-1, 8)
-d = np.diff(ab[:, :6], axis=1)
-print("cols AB CTA: cp.async+wait %.0f  sync %.0f  fft %.0f  sync %.0f  extract %.0f   total %.0f" % (*d.mean(0), (ab[:, 5] - ab[:, 0]).mean()))
-print("  p10/p50/p90 total:", np.percentile(ab[:, 5] - ab[:, 0], [10, 50, 90]))
