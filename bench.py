@@ -256,24 +256,34 @@ def run_engine(args):
             kms, kn = prof.kernel_times()
         prof.close()
         names = ["spectrum_rows", "cols_extract"]
-        per = {names[i]: kms[i] / max(kn[i], 1) for i in range(2)}
-        dom = max(per, key=per.get)
-        ach = ALG_BYTES_KERNEL[dom] * pts_rank / (per[dom] * 1e-3) / 1e9
+        per = {names[i]: kms[i] / max(kn[i], 1) for i in range(2)}              # average duration of ONE launch
+        per_step = {names[i]: kms[i] / K for i in range(2)}                      # kernel time per step (all its launches)
+        launches_per_step = {names[i]: kn[i] / K for i in range(2)}
+        dom = max(per_step, key=per_step.get)
+        pts_per_launch = pts_rank / launches_per_step[dom]                       # the engine issues the batch tile group by tile group
+        ach = ALG_BYTES_KERNEL[dom] * pts_per_launch / (per[dom] * 1e-3) / 1e9
         frame_ms = compute_ms / K
         roof = {
             "bound": "hbm", "kernel": "k_" + dom, "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
             "frac": round(ach / peak, 4), "traffic": None, "peak_source": peak_src,
-            "algorithmic_bytes_per_point": ALG_BYTES_KERNEL[dom],
+            "algorithmic_bytes_per_point": ALG_BYTES_KERNEL[dom], "points_per_launch": int(pts_per_launch),
+            "launches_per_step": launches_per_step,
             "avg_launch_ms": {k: round(v, 4) for k, v in per.items()},
-            "share_of_step": {k: round(v / sum(per.values()), 3) for k, v in per.items()},
+            "share_of_step": {k: round(v / sum(per_step.values()), 3) for k, v in per_step.items()},
+            "timing": "CUDA events around every launch on the launching stream (MW_PROFILE handle, single stream, no overlap "
+                      "between launches), same K steps as the timed region",
             "pipeline": {"algorithmic_bytes_per_point": ALG_BYTES_PIPELINE,
                          "achieved": round(ALG_BYTES_PIPELINE * pts_rank / (frame_ms * 1e-3) / 1e9, 1),
-                         "frac": round(ALG_BYTES_PIPELINE * pts_rank / (frame_ms * 1e-3) / 1e9 / peak, 4)},
+                         "frac": round(ALG_BYTES_PIPELINE * pts_rank / (frame_ms * 1e-3) / 1e9 / peak, 4),
+                         "note": "44 B/pt x points per step / whole-step time of the timed region (both kernels, two streams overlapped)"},
         }
         tr = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tr):
             try:
-                roof["traffic"] = json.load(open(tr)).get("k_" + dom)
+                t = json.load(open(tr)).get("k_" + dom)
+                if t:
+                    roof["traffic"] = t["bytes_per_tile"] * pts_per_launch / (N * N)
+                    roof["traffic_source"] = t["source"]
             except Exception:  # noqa: BLE001
                 pass
 

@@ -1,0 +1,116 @@
+// MistralOceanNative.cs -- P/Invoke declarations for libmistral_ocean.so (include/mistral_ocean.h).
+//
+// Drop this file next to Assets/Mistral Water/Scripts/FFTMesh.cs and put the shared library where Unity's
+// native-plugin loader finds it (Assets/Plugins/x86_64/libmistral_ocean.so).  It could not be compiled in the
+// build image (no dotnet / mono / Unity there); the same exported symbols are exercised through ctypes by
+// mistral-water_b200/native.py and tests/.  Struct layouts are asserted in tests/test_abi.py.
+using System;
+using System.Runtime.InteropServices;
+using UnityEngine;
+
+namespace MistralWater.Native
+{
+    [StructLayout(LayoutKind.Sequential)]
+    public struct MwOceanParams            // mw_ocean_params: FFTMesh's public fields one to one (FFTMesh.cs:9-23)
+    {
+        public int resolution;             // FFTMesh.cs:13
+        public float unitWidth;            // :15
+        public float length;               // :19   must equal resolution * unitWidth
+        public float choppiness;           // :9
+        public float amplitude;            // :23
+        public float windX, windY;         // :21
+        public float tDivision;            // :11
+        public ulong seed;                 // stand-in for UnityEngine.Random's state
+        public int device;                 // CUDA device ordinal
+        public int tiles;                  // independent oceans in this handle (1 for FFTMesh)
+        public uint flags;                 // MW_DEVICE_PTRS = 1, MW_PROFILE = 2
+        public uint reserved;
+    }
+
+    [StructLayout(LayoutKind.Sequential)]
+    public struct MwOceanOut               // mw_ocean_out: IntPtr.Zero = not requested
+    {
+        public IntPtr height;              // float[N*N]
+        public IntPtr disp;                // Vector2[N*N]   hds            (FFTMesh.cs:247)
+        public IntPtr normal;              // Vector3[N*N]   normals        (:246)
+        public IntPtr whitecap;            // float[N*N]
+        public IntPtr jacobian;            // float[N*N]
+        public IntPtr vertices;            // Vector3[N*N]   vertMeow       (:243-245)
+        public IntPtr colors;              // Color[N*N]     colors         (:274)
+    }
+
+    [StructLayout(LayoutKind.Sequential)]
+    public struct MwGerstnerWave { public float dirX, dirY, freq, rate, ampXZ, ampY; }
+
+    [StructLayout(LayoutKind.Sequential)]
+    public struct MwGerstnerParams
+    {
+        public int nWaves, device;
+        public uint flags, reserved;
+        [MarshalAs(UnmanagedType.ByValArray, SizeConst = 64)] public MwGerstnerWave[] waves;
+    }
+
+    public static class MistralOcean
+    {
+        const string Lib = "mistral_ocean";
+        public const int MW_OK = 0, MW_E_INVALID_ARG = -1, MW_E_CUDA = -2, MW_E_OOM = -3, MW_E_STATE = -4, MW_E_NCCL = -5;
+
+        [DllImport(Lib)] public static extern int mw_version();
+        [DllImport(Lib)] static extern IntPtr mw_last_error();
+        public static string LastError() { return Marshal.PtrToStringAnsi(mw_last_error()); }
+
+        [DllImport(Lib)] public static extern int mw_ocean_create(ref MwOceanParams p, out IntPtr handle);
+        [DllImport(Lib)] public static extern void mw_ocean_destroy(IntPtr handle);
+        [DllImport(Lib)] public static extern int mw_ocean_init_spectrum(IntPtr handle);
+        [DllImport(Lib)] public static extern int mw_ocean_set_h0(IntPtr handle, IntPtr h0, IntPtr h0conj);
+        [DllImport(Lib)] public static extern int mw_ocean_get_h0(IntPtr handle, IntPtr h0, IntPtr h0conj);
+        [DllImport(Lib)] public static extern int mw_ocean_get_rest_vertices(IntPtr handle, IntPtr xyz);
+        [DllImport(Lib)] public static extern int mw_ocean_get_dispersion(IntPtr handle, IntPtr omega);
+        [DllImport(Lib)] public static extern int mw_ocean_evolve_spectrum(IntPtr handle, float t, IntPtr htilde);
+        [DllImport(Lib)] public static extern int mw_ocean_generate(IntPtr handle, float t, ref MwOceanOut o);
+        [DllImport(Lib)] public static extern int mw_ocean_update(IntPtr handle, float deltaTime, ref MwOceanOut o);
+        [DllImport(Lib)] public static extern int mw_ocean_reset_timer(IntPtr handle);
+        [DllImport(Lib)] public static extern float mw_ocean_timer(IntPtr handle);
+        [DllImport(Lib)] public static extern int mw_ocean_sync(IntPtr handle);
+        [DllImport(Lib)] public static extern int mw_ocean_set_stream(IntPtr handle, IntPtr cudaStream);
+        [DllImport(Lib)] public static extern int mw_ocean_kernel_times(IntPtr handle, float[] ms, long[] launches, int reset);
+        [DllImport(Lib)] public static extern long mw_kernel_launch_count();
+        [DllImport(Lib)] public static extern int mw_fft2d(int device, int n, int batch, int sign, IntPtr input, IntPtr output);
+        [DllImport(Lib)] public static extern int mw_gerstner_from_material(ref MwGerstnerParams p, float amplitude, float frequency,
+            float steepness, float[] wSpeed, float[] wDirectionAB, float[] wDirectionCD);
+        [DllImport(Lib)] public static extern int mw_gerstner_append_level_one(ref MwGerstnerParams p, float amplitude, float frequency, float steepness);
+        [DllImport(Lib)] public static extern int mw_gerstner_displace(ref MwGerstnerParams p, IntPtr posXyz, IntPtr outXyz, IntPtr outNrm,
+            long n, float t, IntPtr cudaStream);
+
+        public static void Check(int rc) { if (rc != MW_OK) throw new InvalidOperationException("mistral_ocean " + rc + ": " + LastError()); }
+    }
+
+    // The substitution inside FFTMesh.cs (see INTEGRATION.md): bodies of SetParams / GenerateMesh / EvaluateWaves.
+    public sealed class FFTMeshEngine : IDisposable
+    {
+        IntPtr handle;
+        GCHandle hv, hn, hc;               // pinned managed arrays: Vector3[], Vector3[], Color[] are blittable
+        MwOceanOut outBlock;
+
+        public FFTMeshEngine(int resolution, float unitWidth, float length, float choppiness, float amplitude, Vector2 wind,
+                             float tDivision, ulong seed, Vector3[] vertMeow, Vector3[] normals, Color[] colors)
+        {
+            var p = new MwOceanParams { resolution = resolution, unitWidth = unitWidth, length = length, choppiness = choppiness,
+                amplitude = amplitude, windX = wind.x, windY = wind.y, tDivision = tDivision, seed = seed, device = 0, tiles = 1 };
+            MistralOcean.Check(MistralOcean.mw_ocean_create(ref p, out handle));      // FFTMesh.cs:90-99
+            MistralOcean.Check(MistralOcean.mw_ocean_init_spectrum(handle));          // FFTMesh.cs:114-116
+            hv = GCHandle.Alloc(vertMeow, GCHandleType.Pinned);
+            hn = GCHandle.Alloc(normals, GCHandleType.Pinned);
+            hc = GCHandle.Alloc(colors, GCHandleType.Pinned);
+            outBlock = new MwOceanOut { vertices = hv.AddrOfPinnedObject(), normal = hn.AddrOfPinnedObject(), colors = hc.AddrOfPinnedObject() };
+        }
+
+        public void EvaluateWaves(float t) { MistralOcean.Check(MistralOcean.mw_ocean_generate(handle, t, ref outBlock)); }  // FFTMesh.cs:224-280
+
+        public void Dispose()
+        {
+            if (handle != IntPtr.Zero) { MistralOcean.mw_ocean_destroy(handle); handle = IntPtr.Zero; }
+            if (hv.IsAllocated) hv.Free(); if (hn.IsAllocated) hn.Free(); if (hc.IsAllocated) hc.Free();
+        }
+    }
+}
