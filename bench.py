@@ -111,7 +111,8 @@ def run_reference(args):
     from oracle import cref
     cref.build()
     N = args.resolution
-    threads = cref.max_threads()
+    # all host threads, whatever OMP_NUM_THREADS says (torchrun sets it to 1)
+    threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     per_vertex_s = 1.0e-7 * N * N  # ~100 ns per inner term
     verts = max(threads, int(round(args.ref_step_seconds * threads / per_vertex_s)))
     for _ in range(args.warmup):
@@ -134,7 +135,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args, world):
@@ -182,14 +183,17 @@ def run_engine(args):
         torch.cuda.synchronize()
 
     def step(k):
-        # everything is ordered on `stream`: the two engine kernels, then (N > 1) the all-gather
-        st.generate_local(0.016 * k)
+        # N = 1: the engine's kernels on `stream`.  N > 1: the same, then the path's one collective -- the
+        # all-gather of frame k runs on a communication stream under the generation of frame k + 1
         if world > 1:
-            st.all_gather()
+            st.generate_pipelined(0.016 * k)
+        else:
+            st.generate_local(0.016 * k)
 
     with torch.cuda.stream(stream):
         for k in range(W):
             step(k)
+        st.finish()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         launches0 = mw.native.launch_count()
@@ -197,6 +201,7 @@ def run_engine(args):
             e0.record(stream)
             for k in range(K):
                 step(W + k)
+            st.finish()          # (N > 1) the last gathers are inside the timed region
             e1.record(stream)
             barrier()
             ms = e0.elapsed_time(e1)
@@ -206,6 +211,7 @@ def run_engine(args):
             while len(clk.samples) < 8 and extra < 200:
                 for k in range(8):
                     step(k)
+                st.finish()
                 torch.cuda.synchronize()
                 extra += 1
         clocks = clk.summary()
@@ -325,7 +331,7 @@ def run_engine(args):
         cpu = {"value": rate, "unit": UNIT, "cores": 1, "kind": "port",
                "sample": f"{verts} of {N * N} vertices of the same {N}x{N} grid through the literal "
                          f"FFTMesh.Displacement loop (oracle/ref_fftmesh.c), 1 thread as Unity runs it; {dt:.1f} s",
-               "host_threads_available": cref.max_threads()}
+               "host_threads_available": len(os.sched_getaffinity(0))}
 
     if rank == 0:
         line = {
@@ -344,13 +350,43 @@ def run_engine(args):
                 "allgather_busbw_gbs": round(slot * (world - 1) / (gather_ms / K * 1e-3) / 1e9, 1) if gather_ms else None,
                 "nvlink_peer_copy_peak_gbs": 770.0,
             }
-        print(json.dumps(line), flush=True)
+        emit(line)
     st.close()
     if world > 1:
         dist.destroy_process_group()
 
 
+class _CleanStdout:
+    """Library chatter (e.g. "NCCL version ...") must not share stdout with the one JSON line: while active,
+    fd 1 points at stderr; emit() writes to the real stdout."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.real = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def emit(self, text):
+        os.write(self.real, (text + "\n").encode())
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.real, 1)
+        os.close(self.real)
+
+
+_OUT = None
+
+
+def emit(line):
+    if _OUT is not None:
+        _OUT.emit(json.dumps(line))
+    else:
+        print(json.dumps(line), flush=True)
+
+
 def main():
+    global _OUT
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
@@ -363,10 +399,12 @@ def main():
     ap.add_argument("--ref-step-seconds", type=float, default=1.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_engine(args)
+    with _CleanStdout() as out:
+        _OUT = out
+        if args.impl == "reference":
+            run_reference(args)
+        else:
+            run_engine(args)
 
 
 if __name__ == "__main__":

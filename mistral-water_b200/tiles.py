@@ -78,7 +78,13 @@ class ShardedTiles:
         self.layout = TileLayout(N, world, tiles_per_rank)
         self.rank, self.world, self.group = rank, world, group
         self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
-        self.gather = torch.empty((world, self.layout.slot_floats), dtype=torch.float32, device=self.device)
+        # two gather buffers: the all-gather of frame k (communication stream) overlaps the generation of
+        # frame k + 1 (engine stream) -- see generate_pipelined()
+        self.nbuf = 2 if world > 1 else 1
+        self.gathers = [torch.empty((world, self.layout.slot_floats), dtype=torch.float32, device=self.device)
+                        for _ in range(self.nbuf)]
+        self.gather = self.gathers[0]
+        self._frame = 0
         self.rank_params = dict(resolution=N, unit_width=unit_width, choppiness=choppiness, amplitude=amplitude,
                                 wind=tile_wind(wind, self.layout.global_tile(rank, 0)),
                                 seed=base_seed + self.layout.global_tile(rank, 0), tiles=tiles_per_rank)
@@ -100,9 +106,9 @@ class ShardedTiles:
 
         return run
 
-    def slot_views(self, rank: int | None = None) -> dict:
-        """Field views into one rank's slot (default: ours)."""
-        slot = self.gather[self.rank if rank is None else rank]
+    def slot_views(self, rank: int | None = None, buf: int = 0) -> dict:
+        """Field views into one rank's slot (default: ours) of gather buffer `buf`."""
+        slot = self.gathers[buf][self.rank if rank is None else rank]
         out = {}
         for name, comps in FIELDS:
             b, e = self.layout.field_range(name)
@@ -128,6 +134,42 @@ class ShardedTiles:
             torch.cuda.current_stream(self.device).wait_stream(self.stream)  # NCCL runs after the producer
         self.all_gather()
         return self.gather
+
+    def generate_pipelined(self, t: float):
+        """Frame k: generate into gather buffer k % 2 on the engine stream, then all-gather it on a separate
+        communication stream, so that the collective of frame k runs under the generation of frame k + 1.
+        Returns the buffer being gathered; call finish() before reading it."""
+        torch = self.torch
+        if self.world == 1 or not hasattr(self, "stream"):
+            return self.generate(t)
+        if not hasattr(self, "comm_stream"):
+            self.comm_stream = torch.cuda.Stream(device=self.device)
+            self._ev_gen = [torch.cuda.Event() for _ in range(2)]
+            self._ev_comm = [torch.cuda.Event() for _ in range(2)]
+            self._comm_used = [False, False]
+        b = self._frame & 1
+        self._frame += 1
+        if self._comm_used[b]:
+            self.stream.wait_event(self._ev_comm[b])      # buffer b is free again once its last gather is done
+        self._gen(float(t), self.slot_views(buf=b))
+        self._ev_gen[b].record(self.stream)
+        import torch.distributed as dist
+        with torch.cuda.stream(self.comm_stream):
+            self.comm_stream.wait_event(self._ev_gen[b])
+            g = self.gathers[b]
+            dist.all_gather_into_tensor(g.view(-1), g[self.rank].view(-1), group=self.group)
+            self._ev_comm[b].record(self.comm_stream)
+        self._comm_used[b] = True
+        self.gather = self.gathers[b]
+        return self.gather
+
+    def finish(self) -> None:
+        """Make the current stream wait for everything generate_pipelined() queued."""
+        torch = self.torch
+        if hasattr(self, "comm_stream"):
+            cur = torch.cuda.current_stream(self.device)
+            cur.wait_stream(self.comm_stream)
+            cur.wait_stream(self.stream)
 
     def tile_view(self, global_tile: int, name: str):
         """Field `name` of any tile, from the gathered buffer: [N*N, comps]."""
