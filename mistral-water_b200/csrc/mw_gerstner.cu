@@ -21,7 +21,9 @@ struct GerstnerTable {
 // MUFU approximations (abs. error ~5e-7 on the reduced range).  |theta| stays far below 2^17 here.
 __device__ __forceinline__ void sincos_reduced(float th, float* s, float* c)
 {
-    const float k = rintf(th * 0.15915494309189535f);  // theta / 2pi
+    // round-to-nearest of theta / 2pi by the add-magic trick (|theta / 2pi| < 2^22): two FADDs on the FMA pipe
+    // instead of an FRND on the XU pipe, which sin and cos (MUFU) already saturate
+    const float k = __fadd_rn(__fadd_rn(th * 0.15915494309189535f, 12582912.0f), -12582912.0f);
     float r = fmaf(k, -6.28125f, th);                  // 2pi = 6.28125 + 1.9350051879882812e-3 + 3.019916050561733e-7
     r = fmaf(k, -1.9350051879882812e-3f, r);
     r = fmaf(k, -3.019916050561733e-7f, r);

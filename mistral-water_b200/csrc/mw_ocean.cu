@@ -55,9 +55,9 @@ struct mw_ocean {
     // tile-group pipelining: the frame is issued as groups of `group_tiles` tiles, alternating between two
     // streams and two slots of the intermediate buffer, so that (a) the intermediate of a group stays in the
     // 126 MB L2 between pass 1 and pass 2 and (b) pass 1 of one group overlaps pass 2 of the previous one
-    int group_tiles = 1, x_tiles = 1;
-    cudaStream_t aux_stream = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    int group_tiles = 1, x_tiles = 1, slots = 2;
+    cudaStream_t aux_stream[3] = {nullptr, nullptr, nullptr};   // streams 1..slots-1 (stream 0 is the caller's)
+    cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
     long long* dbg_rows = nullptr; long long* dbg_cols = nullptr;  // developer phase timing (mw_debug_phase_buffers)
     // profiling
     std::vector<EvPair> ev_pool; size_t ev_used = 0;
@@ -170,16 +170,19 @@ extern "C" int mw_ocean_create(const mw_ocean_params* params, mw_ocean** out)
         if (gt < 1) gt = 1;
         if (gt > o->tiles) gt = o->tiles;
         o->group_tiles = (int)gt;
-        o->x_tiles = o->tiles <= o->group_tiles ? o->tiles : 2 * o->group_tiles;
+        if (const char* e = getenv("MW_SLOTS")) o->slots = atoi(e);
+        if (o->slots < 2) o->slots = 2;
+        if (o->slots > 4) o->slots = 4;
+        o->x_tiles = o->tiles <= o->group_tiles ? o->tiles : o->slots * o->group_tiles;
         char* x = nullptr;  // one allocation: 28 B per grid point of x_tiles tiles
         if ((rc = ensure(&x, o->n2 * o->x_tiles * 28))) return fail(rc);
         o->XAB = reinterpret_cast<float4*>(x);
         o->XC = reinterpret_cast<float2*>(x + o->n2 * o->x_tiles * 20);
-        if (cudaStreamCreateWithFlags(&o->aux_stream, cudaStreamNonBlocking) != cudaSuccess ||
-            cudaEventCreateWithFlags(&o->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-            cudaEventCreateWithFlags(&o->ev_join, cudaEventDisableTiming) != cudaSuccess) {
-            mw_set_error("stream/event creation failed"); return fail(MW_E_CUDA);
-        }
+        bool ok = cudaEventCreateWithFlags(&o->ev_fork, cudaEventDisableTiming) == cudaSuccess;
+        for (int i = 0; i < o->slots - 1 && ok; ++i)
+            ok = cudaStreamCreateWithFlags(&o->aux_stream[i], cudaStreamNonBlocking) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&o->ev_join[i], cudaEventDisableTiming) == cudaSuccess;
+        if (!ok) { mw_set_error("stream/event creation failed"); return fail(MW_E_CUDA); }
     }
 
     // small host-built tables
@@ -224,9 +227,11 @@ extern "C" void mw_ocean_destroy(mw_ocean* o)
     void* ptrs[] = {o->spec, o->omega, o->ramp, o->kd, o->tw, o->XAB, o->s_height, o->s_disp, o->s_normal,
                     o->s_white, o->s_jac, o->s_vert, o->s_col, o->s_h};
     for (void* q : ptrs) if (q) cudaFree(q);
-    if (o->aux_stream) { cudaStreamSynchronize(o->aux_stream); cudaStreamDestroy(o->aux_stream); }
+    for (int i = 0; i < 3; ++i) {
+        if (o->aux_stream[i]) { cudaStreamSynchronize(o->aux_stream[i]); cudaStreamDestroy(o->aux_stream[i]); }
+        if (o->ev_join[i]) cudaEventDestroy(o->ev_join[i]);
+    }
     if (o->ev_fork) cudaEventDestroy(o->ev_fork);
-    if (o->ev_join) cudaEventDestroy(o->ev_join);
     if (o->own_stream) cudaStreamDestroy(o->own_stream);
     delete o;
 }
@@ -408,17 +413,18 @@ static int run_frame_n(mw_ocean* o, mwk::RowArgs ra, mwk::ColArgs ca)
     const int ngroups = (o->tiles + G - 1) / G;
     // MW_PROFILE handles stay on one stream so that the per-kernel event times are not overlapped
     const bool dual = ngroups > 1 && !o->profile;
+    const int S = o->slots;
     if (dual) {
         MW_CUDA(cudaEventRecord(o->ev_fork, o->stream));
-        MW_CUDA(cudaStreamWaitEvent(o->aux_stream, o->ev_fork, 0));
+        for (int i = 0; i < S - 1; ++i) MW_CUDA(cudaStreamWaitEvent(o->aux_stream[i], o->ev_fork, 0));
     }
     float4* xab0 = o->XAB;
     float2* xc0 = o->XC;
     for (int gi = 0; gi < ngroups; ++gi) {
         const int t0 = gi * G;
         const int nt = o->tiles - t0 < G ? o->tiles - t0 : G;
-        const int slot = ngroups > 1 ? (gi & 1) : 0;
-        cudaStream_t st = (dual && (gi & 1)) ? o->aux_stream : o->stream;
+        const int slot = ngroups > 1 ? (gi % S) : 0;
+        cudaStream_t st = (dual && slot) ? o->aux_stream[slot - 1] : o->stream;
         ra.tile0 = ca.tile0 = t0;
         ra.XAB = xab0 + (size_t)slot * G * o->n2 * 5 / 4;
         ra.XC = xc0 + (size_t)slot * G * o->n2;
@@ -428,8 +434,10 @@ static int run_frame_n(mw_ocean* o, mwk::RowArgs ra, mwk::ColArgs ca)
         if ((rc = launch_cols<N, CMINB>(o, ca, nt, st))) return rc;
     }
     if (dual) {
-        MW_CUDA(cudaEventRecord(o->ev_join, o->aux_stream));
-        MW_CUDA(cudaStreamWaitEvent(o->stream, o->ev_join, 0));
+        for (int i = 0; i < S - 1; ++i) {
+            MW_CUDA(cudaEventRecord(o->ev_join[i], o->aux_stream[i]));
+            MW_CUDA(cudaStreamWaitEvent(o->stream, o->ev_join[i], 0));
+        }
     }
     return MW_OK;
 }

@@ -236,29 +236,35 @@ __global__ void __launch_bounds__(RP * 3 * (N / 16), MINB) k_spectrum_rows(const
         const float k2A = kxA * kxA + kzm * kzm, k2B = kxB * kxB + kzm * kzm;
         const float invA = k2A < MW_EPSILON_F * MW_EPSILON_F ? 0.0f : rsqrtf(k2A);  // FFTMesh.cs:213-214
         const float invB = k2B < MW_EPSILON_F * MW_EPSILON_F ? 0.0f : rsqrtf(k2B);
-        // packing multipliers with the output signs folded in (see "Signs" above)
-        const float2 k1 = make_float2(-kxA, -kzm), k2 = make_float2(-kxB, -kzmm), k3 = make_float2(-kxA, -kzmm), k4 = make_float2(-kxB, -kzm);
-        const float2 u1 = make_float2(-kxA * invA, kzm * invA), u3 = make_float2(-kxA * invA, kzmm * invA);
-        const float2 u2 = make_float2(-kxB * invB, kzmm * invB), u4 = make_float2(-kxB * invB, kzm * invB);
-        float2 A1, A2, A3, A4, B1, B2, B3, B4;
+        // packing multipliers with the output signs folded in (see "Signs" above), as packed pairs:
+        // lane x = the A' multiplier (-ux + i uz), lane y = the B' multiplier (-kx - i kz), so that one packed
+        // complex multiply serves both fields and the result IS the (A.re, B.re, A.im, B.im) line element
+        const float uxA = -kxA * invA, uxB = -kxB * invB;
+        const mwfft::cpk M1 = {make_float2(uxA, -kxA), make_float2(kzm * invA, -kzm)};    // P1 = (rA, m)
+        const mwfft::cpk M3 = {make_float2(uxA, -kxA), make_float2(kzmm * invA, -kzmm)};  // P3 = (rA, m')
+        const mwfft::cpk M2 = {make_float2(uxB, -kxB), make_float2(kzmm * invB, -kzmm)};  // P2 = (rB, m')
+        const mwfft::cpk M4 = {make_float2(uxB, -kxB), make_float2(kzm * invB, -kzm)};    // P4 = (rB, m)
+        // F = (M_self * E_self - M_partner * conj(E_partner)) * (-i/2)   (herm_pack, both lanes at once)
+        auto pack2 = [](const mwfft::cpk& ms, float2 es, const mwfft::cpk& mp, float2 ep) {
+            const mwfft::cpk d = mwfft::psub(mwfft::pmul(ms, es.x, es.y), mwfft::pmul(mp, ep.x, -ep.y));
+            const float2 h = make_float2(0.5f, 0.5f), nh = make_float2(-0.5f, -0.5f);
+            return make_float4(d.im.x * h.x, d.im.y * h.y, d.re.x * nh.x, d.re.y * nh.y);
+        };
+        float4 F1, F2, F3, F4;
         if (!special) {  // partners: P1 <-> P2, P3 <-> P4
-            A1 = herm_pack(u1, E1, u2, E2); A2 = herm_pack(u2, E2, u1, E1);
-            A3 = herm_pack(u3, E3, u4, E4); A4 = herm_pack(u4, E4, u3, E3);
-            B1 = herm_pack(k1, E1, k2, E2); B2 = herm_pack(k2, E2, k1, E1);
-            B3 = herm_pack(k3, E3, k4, E4); B4 = herm_pack(k4, E4, k3, E3);
+            F1 = pack2(M1, E1, M2, E2); F2 = pack2(M2, E2, M1, E1);
+            F3 = pack2(M3, E3, M4, E4); F4 = pack2(M4, E4, M3, E3);
         } else {         // partners: P1 <-> P3, P4 <-> P2
-            A1 = herm_pack(u1, E1, u3, E3); A3 = herm_pack(u3, E3, u1, E1);
-            A4 = herm_pack(u4, E4, u2, E2); A2 = herm_pack(u2, E2, u4, E4);
-            B1 = herm_pack(k1, E1, k3, E3); B3 = herm_pack(k3, E3, k1, E1);
-            B4 = herm_pack(k4, E4, k2, E2); B2 = herm_pack(k2, E2, k4, E4);
+            F1 = pack2(M1, E1, M3, E3); F3 = pack2(M3, E3, M1, E1);
+            F4 = pack2(M4, E4, M2, E2); F2 = pack2(M2, E2, M4, E4);
         }
         // line positions shifted by N/2: the transform then carries the (-1)^b of sigma
         const int pm = pad_idx((m + N / 2) & (N - 1)), pmm = pad_idx((mm + N / 2) & (N - 1));
         // line 0 = (A,B) of row rA ; line 1 = (A,B) of row rB ; line 2 = (C of rA, C of rB)
-        lines[pm] = make_float4(A1.x, B1.x, A1.y, B1.y);
-        lines[pmm] = make_float4(A3.x, B3.x, A3.y, B3.y);
-        lines[LP + pm] = make_float4(A4.x, B4.x, A4.y, B4.y);
-        lines[LP + pmm] = make_float4(A2.x, B2.x, A2.y, B2.y);
+        lines[pm] = F1;
+        lines[pmm] = F3;
+        lines[LP + pm] = F4;
+        lines[LP + pmm] = F2;
         lines[2 * LP + pm] = make_float4(-E1.x, -E4.x, -E1.y, -E4.y);
         lines[2 * LP + pmm] = make_float4(-E3.x, -E2.x, -E3.y, -E2.y);
     }
@@ -322,6 +328,13 @@ struct ColArgs {
                         // blockIdx.x >= ab_blocks : C slab of 8 columns
 };
 
+__device__ __forceinline__ float sqrt_approx(float x)
+{
+    float r;
+    asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));  // MUFU.SQRT, ~1 ulp: the whitecap tolerance is 1e-5 of the Jacobian scale
+    return r;
+}
+
 // 5 packed lines per CTA, two kinds of CTA in one launch:
 //   (A,B) CTA: the (A,B) pairs of 4 columns + the halo column b0 + 4 (so that hds[index + 1] of
 //              FFTMesh.cs:266 is on chip)  -> hds, normal, Jacobian, whitecap
@@ -374,6 +387,7 @@ __global__ void __launch_bounds__(5 * (N / 16), MINB) k_cols_extract(const ColAr
     // transforms zeros: same instruction stream for every thread, no divergent barrier
     const bool active = is_ab ? (!is_halo || (want_white && b0 + W < N)) : !is_halo;
     if ((a.dbg_flags & 8) && !is_ab) return;
+    if (T >= 32 && !active) return;  // whole warps with nothing to transform: exited threads are not waited for by barriers
 
     // ---- first-stage inputs straight from global memory: line position p = g + T k holds intermediate row
     //      (p + N/2) mod N = g + T ((k + 8) mod 16)  (the (-1)^a of sigma); slab-major layout => contiguous ----
@@ -428,6 +442,7 @@ __global__ void __launch_bounds__(5 * (N / 16), MINB) k_cols_extract(const ColAr
     }
     __syncthreads();
     MW_STAMP(3);
+    if (T >= 32 && is_halo) return;  // whole warps: done (for T < 32 they share a warp with owners and stay for the shuffles)
     {
         const bool own = !is_halo && !(a.dbg_flags & 1);  // halo threads run the same code with every memory access predicated off
         if (a.dbg_flags & 16) return;
@@ -470,7 +485,7 @@ __global__ void __launch_bounds__(5 * (N / 16), MINB) k_cols_extract(const ColAr
                 if (a.whitecap) {
                     // noise = |(|n.x|, |n.z|) * 0.3|   (:269-270)
                     const float ax = fabsf(nx) * 0.3f, az = fabsf(nz) * 0.3f;
-                    float turb = fmaxf(1.0f - jac + sqrtf(ax * ax + az * az), 0.0f);  // :270
+                    float turb = fmaxf(1.0f - jac + sqrt_approx(ax * ax + az * az), 0.0f);  // :270
                     turb = fminf(turb, 1.0f);                                          // SmoothStep clamps
                     a.whitecap[o] = -2.0f * turb * turb * turb + 3.0f * turb * turb;   // :273
                 }

@@ -211,6 +211,52 @@ def test_tiles_are_independent_and_match_single_handles(mw):
             assert np.array_equal(batch[name][k], one[name][0]), (k, name)
 
 
+def test_tile_group_pipeline_matches_single_handles(mw):
+    """tiles > group size: the frame is issued group by group on two streams with a double-buffered
+    intermediate.  Odd group count, repeated frames, every tile must equal its own handle."""
+    N, T = 1024, 3
+    with mw.Ocean(N, seed=500, tiles=T) as o:
+        o.init_spectrum()
+        first = o.generate(0.25)
+        again = o.generate(0.25)
+        other = o.generate(2.0)
+    for name in first:
+        assert np.array_equal(first[name], again[name]), name
+        assert not np.array_equal(first[name], other[name]), name
+    for k in range(T):
+        with mw.Ocean(N, seed=500 + k) as s:
+            s.init_spectrum()
+            one = s.generate(0.25)
+        for name in ("height", "disp", "normal", "whitecap"):
+            assert np.array_equal(first[name][k], one[name][0]), (k, name)
+
+
+def test_update_timer_semantics_through_the_abi(mw):
+    """mw_ocean_update == FFTMesh.Update: timer += dt / tDivision; EvaluateWaves(timer)  (FFTMesh.cs:70-72)."""
+    with mw.Ocean(64, seed=3, t_division=4.0) as o:
+        o.init_spectrum()
+        bufs = o.alloc_outputs()
+        o.update(1.0, bufs)
+        o.update(0.5, bufs)
+        assert abs(o.timer - 0.375) < 1e-7
+        ref = o.generate(0.375)
+        for k in bufs:
+            assert np.array_equal(bufs[k], ref[k]), k
+        o.reset_timer()
+        assert o.timer == 0.0
+
+
+def test_smallest_and_jacobian_only(mw, cref, r64):
+    N = 32
+    p = cref.params(N)
+    _, h0, hc = cref.generate_mesh(p, seed=8)
+    ref = r64.evaluate_waves(h0, hc, N, p.length, p.unit_width, p.choppiness, 0.9)
+    with mw.Ocean(N) as o:
+        o.set_h0(h0, hc)
+        out = o.generate(0.9, names=("jacobian",))
+    assert max_abs(out["jacobian"], ref["jacobian"]) <= 1e-5 * max(1.0, float(np.abs(ref["jacobian"]).max()))
+
+
 def test_device_pointer_mode_matches_host_mode(mw):
     import torch
     N = 512
