@@ -46,8 +46,8 @@ struct mw_ocean {
     float2* ramp = nullptr;   // [2N]
     float* kd = nullptr;      // [N]
     float2* tw = nullptr;     // [N]
-    float4* XAB = nullptr;    // [tiles][N/4][N][5] intermediate, fields A and B + halo copies (20 B / point)
-    float2* XC = nullptr;     // [tiles][N/8][N][8] intermediate, field C (8 B / point); lives right behind XAB
+    float4* XAB = nullptr;    // [tiles][N/8][N][9] intermediate, fields A and B + halo copies (18 B / point)
+    float2* XC = nullptr;     // [tiles][N/16][N][16] intermediate, field C (8 B / point); lives right behind XAB
     // scratch outputs (host-pointer mode, or inputs of k_mesh_outputs)
     float* s_height = nullptr; float2* s_disp = nullptr; float* s_normal = nullptr; float* s_white = nullptr;
     float* s_jac = nullptr; float* s_vert = nullptr; float4* s_col = nullptr; float2* s_h = nullptr;
@@ -164,8 +164,8 @@ extern "C" int mw_ocean_create(const mw_ocean_params* params, mw_ocean** out)
     if ((rc = ensure(&o->kd, (size_t)N))) return fail(rc);
     if ((rc = ensure(&o->tw, (size_t)N))) return fail(rc);
     {
-        // group size: keep one group's intermediate (28 B per point) around 32 MB
-        long long gt = (32ll << 20) / (long long)(o->n2 * 28);
+        // group size: keep one group's intermediate (26 B per point) around 32 MB
+        long long gt = (32ll << 20) / (long long)(o->n2 * 26);
         if (const char* e = getenv("MW_GROUP_TILES")) gt = atoll(e);
         if (gt < 1) gt = 1;
         if (gt > o->tiles) gt = o->tiles;
@@ -174,10 +174,11 @@ extern "C" int mw_ocean_create(const mw_ocean_params* params, mw_ocean** out)
         if (o->slots < 2) o->slots = 2;
         if (o->slots > 4) o->slots = 4;
         o->x_tiles = o->tiles <= o->group_tiles ? o->tiles : o->slots * o->group_tiles;
-        char* x = nullptr;  // one allocation: 28 B per grid point of x_tiles tiles
-        if ((rc = ensure(&x, o->n2 * o->x_tiles * 28))) return fail(rc);
+        char* x = nullptr;  // one allocation: 18 + 8 B per grid point of x_tiles tiles
+        const size_t xab_bytes = mwk::xab_tile_elems(o->N) * sizeof(float4) * o->x_tiles;
+        if ((rc = ensure(&x, xab_bytes + o->n2 * o->x_tiles * 8))) return fail(rc);
         o->XAB = reinterpret_cast<float4*>(x);
-        o->XC = reinterpret_cast<float2*>(x + o->n2 * o->x_tiles * 20);
+        o->XC = reinterpret_cast<float2*>(x + xab_bytes);
         bool ok = cudaEventCreateWithFlags(&o->ev_fork, cudaEventDisableTiming) == cudaSuccess;
         for (int i = 0; i < o->slots - 1 && ok; ++i)
             ok = cudaStreamCreateWithFlags(&o->aux_stream[i], cudaStreamNonBlocking) == cudaSuccess &&
@@ -385,8 +386,10 @@ static int launch_rows(mw_ocean* o, const mwk::RowArgs& a, int ntiles, cudaStrea
 template <int N, int MINB>
 static int launch_cols(mw_ocean* o, mwk::ColArgs a, int ntiles, cudaStream_t st)
 {
-    constexpr int threads = 5 * (N / 16);
-    constexpr size_t smem = mwfft::Plan<N>::TW_BYTES + (size_t)5 * mwfft::line_pitch(N, 4) * sizeof(float4);
+    constexpr int W = mwk::slab_w(N);
+    constexpr int threads = (W + 1) * (N / 16);
+    constexpr size_t smem = mwfft::Plan<N>::TW_BYTES + (size_t)(W + 1) * mwfft::line_pitch(N, W) * sizeof(float4) +
+                            (size_t)((threads + 31) / 32) * 96 * sizeof(float);
     static bool attr_done[64] = {};
     if (!attr_done[o->p.device]) {
         MW_CUDA(cudaFuncSetAttribute(mwk::k_cols_extract<N, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -395,8 +398,8 @@ static int launch_cols(mw_ocean* o, mwk::ColArgs a, int ntiles, cudaStream_t st)
         attr_done[o->p.device] = true;
     }
     const bool want_ab = a.disp || a.normal || a.whitecap || a.jacobian;
-    a.ab_blocks = want_ab ? N / 4 : 0;
-    const int c_blocks = a.height ? N / 8 : 0;
+    a.ab_blocks = want_ab ? N / W : 0;
+    const int c_blocks = a.height ? N / (2 * W) : 0;
     if (a.ab_blocks + c_blocks == 0) return MW_OK;
     dim3 grid(a.ab_blocks + c_blocks, ntiles);
     ProfScope ps(o, 1);
@@ -426,7 +429,7 @@ static int run_frame_n(mw_ocean* o, mwk::RowArgs ra, mwk::ColArgs ca)
         const int slot = ngroups > 1 ? (gi % S) : 0;
         cudaStream_t st = (dual && slot) ? o->aux_stream[slot - 1] : o->stream;
         ra.tile0 = ca.tile0 = t0;
-        ra.XAB = xab0 + (size_t)slot * G * o->n2 * 5 / 4;
+        ra.XAB = xab0 + (size_t)slot * G * mwk::xab_tile_elems(o->N);
         ra.XC = xc0 + (size_t)slot * G * o->n2;
         ca.XAB = ra.XAB;
         ca.XC = ra.XC;
@@ -448,11 +451,11 @@ static int run_frame(mw_ocean* o, const mwk::RowArgs& ra, const mwk::ColArgs& ca
         case 32: return run_frame_n<32, 16, 1, 1>(o, ra, ca);
         case 64: return run_frame_n<64, 8, 1, 1>(o, ra, ca);
         case 128: return run_frame_n<128, 8, 1, 1>(o, ra, ca);
-        case 256: return run_frame_n<256, 4, 2, 2>(o, ra, ca);
-        case 512: return run_frame_n<512, 2, 2, 2>(o, ra, ca);
+        case 256: return run_frame_n<256, 4, 2, 1>(o, ra, ca);
+        case 512: return run_frame_n<512, 2, 2, 1>(o, ra, ca);
         case 1024: {
             static const int minb = getenv("MW_ROWS_MINB") ? atoi(getenv("MW_ROWS_MINB")) : 3;
-            return minb == 3 ? run_frame_n<1024, 1, 3, 2>(o, ra, ca) : run_frame_n<1024, 1, 4, 2>(o, ra, ca);
+            return minb == 3 ? run_frame_n<1024, 1, 3, 1>(o, ra, ca) : run_frame_n<1024, 1, 4, 1>(o, ra, ca);
         }
         case 2048: return run_frame_n<2048, 1, 1, 1>(o, ra, ca);
     }

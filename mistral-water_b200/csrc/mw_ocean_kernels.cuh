@@ -142,21 +142,33 @@ __global__ void k_evolve(const float4* __restrict__ spec, const float* __restric
 // Intermediate layout (ours to choose), SLAB-MAJOR so that what one pass-2 CTA reads is one contiguous
 // block of memory (a row-major intermediate makes pass 2 read 64-byte pieces 16 KB apart, which runs the
 // HBM at a fraction of its bandwidth -- measured):
-//   XAB[tile][b / 4][n][5] : float4 (A.re, B.re, A.im, B.im), A = chop-displacement field, B = slope field;
-//                            entries 0..3 = columns 4s..4s+3 of row n, entry 4 = a copy of column 4s+4
-//                            (the halo the Jacobian's forward difference needs)        20 B per grid point
-//   XC [tile][b / 8][n][8] : float2 (C.re, C.im), C = height field                       8 B per grid point
-// Pass 1 therefore scatters 64-byte pieces (writes: they are merged in the 126 MB L2 before they reach HBM).
-__host__ __device__ constexpr size_t xab_index(int N, int n, int b) { return ((size_t)(b >> 2) * N + n) * 5 + (b & 3); }
-__host__ __device__ constexpr size_t xc_index(int N, int n, int b) { return ((size_t)(b >> 3) * N + n) * 8 + (b & 7); }
+//   XAB[tile][b / 8][n][9]   : float4 (A.re, B.re, A.im, B.im), A = chop-displacement field, B = slope field;
+//                              entries 0..7 = columns 8s..8s+7 of row n, entry 8 = a copy of column 8s+8
+//                              (the halo the Jacobian's forward difference needs)      18 B per grid point
+//   XC [tile][b / 16][n][16] : float2 (C.re, C.im), C = height field                     8 B per grid point
+// Pass 1 therefore scatters 128-byte pieces (writes: they are merged in the 126 MB L2 before they reach HBM).
+// Slabs are 8 (16) columns wide because pass 2 must WRITE its outputs in rows of that many columns: measured
+// (tools/ubench/store_pattern.cu), 4-column output rows leave half-filled 32-byte sectors (whitecap 16 B,
+// normal 48 B per row) and the same bytes take 224 us instead of 71 us (8 columns) per 16 tiles.
+// (N = 2048: 4-column slabs -- nine 2048-point packed lines do not fit in shared memory.)
+__host__ __device__ constexpr int slab_w(int N) { return N <= 1024 ? 8 : 4; }
+__host__ __device__ constexpr size_t xab_index(int N, int n, int b)
+{
+    return ((size_t)(b / slab_w(N)) * N + n) * (slab_w(N) + 1) + (b % slab_w(N));
+}
+__host__ __device__ constexpr size_t xc_index(int N, int n, int b)
+{
+    return ((size_t)(b / (2 * slab_w(N))) * N + n) * (2 * slab_w(N)) + (b % (2 * slab_w(N)));
+}
+__host__ __device__ constexpr size_t xab_tile_elems(int N) { return (size_t)(N / slab_w(N)) * N * (slab_w(N) + 1); }
 struct RowArgs {
     const float4* spec;    // [tiles][N][N]  (h0, h0conj)
     const float* omega;    // [N][N]
     const float2* ramp;    // [2N]  exp(i pi s (1-N)/N), s = n + m
     const float* kd;       // [N]   2 pi (i - N/2) / L, fp32 as FFTMesh.cs:201
     const float2* tw;      // [N]   exp(+2 pi i x / N)
-    float4* XAB;           // [tiles][N/4][N][5]
-    float2* XC;            // [tiles][N/8][N][8]
+    float4* XAB;           // [tiles][N/8][N][9]
+    float2* XC;            // [tiles][N/16][N][16]
     float t;
     int tile0;             // first tile of this launch (blockIdx.y counts from it); X is indexed by blockIdx.y
     long long* dbg;        // developer phase-timing buffer (NULL in production)
@@ -287,14 +299,14 @@ __global__ void __launch_bounds__(RP * 3 * (N / 16), MINB) k_spectrum_rows(const
         mwfft::fft_line_inreg<N, +1>(v, line, g, tw2, tw3, line_sync);
         if (q < 2) {
             const int row = q ? rB : rA;
-            float4* dst = a.XAB + (size_t)xt * N * N * 5 / 4;
+            float4* dst = a.XAB + (size_t)xt * xab_tile_elems(N);
 #pragma unroll
             for (int sl = 0; sl < 16; ++sl) {
                 const int idx = mwfft::final_idx<N>(g, sl);
                 const float4 e = make_float4(v[sl].re.x, v[sl].re.y, v[sl].im.x, v[sl].im.y);
                 const size_t at = xab_index(N, row, idx);
                 dst[at] = e;
-                if ((idx & 3) == 0 && idx != 0) dst[at - (size_t)N * 5 + 4] = e;  // halo copy for the slab to the west
+                if ((idx % slab_w(N)) == 0 && idx != 0) dst[at - (size_t)N * (slab_w(N) + 1) + slab_w(N)] = e;  // halo copy for the slab to the west
             }
         } else {
             float2* dst = a.XC + (size_t)xt * N * N;
@@ -313,8 +325,8 @@ __global__ void __launch_bounds__(RP * 3 * (N / 16), MINB) k_spectrum_rows(const
 // pass 2: column FFT + extraction (+ Jacobian whitecap)
 // =============================================================================================
 struct ColArgs {
-    const float4* XAB;  // [tiles][N/4][N][5]
-    const float2* XC;   // [tiles][N/8][N][8]
+    const float4* XAB;  // [tiles][N/8][N][9]
+    const float2* XC;   // [tiles][N/16][N][16]
     const float2* tw;   // [N]
     float* height;      // [tiles][N*N]     or NULL
     float2* disp;       // [tiles][N*N]     or NULL   (hds)
@@ -324,51 +336,63 @@ struct ColArgs {
     long long* dbg;     // developer phase-timing buffer (NULL in production): 8 clock64 stamps per CTA
     int dbg_flags;      // developer experiments (tools/phase_timing.py)
     int tile0;          // first tile of this launch (outputs are indexed by tile0 + blockIdx.y, X by blockIdx.y)
-    int ab_blocks;      // blockIdx.x <  ab_blocks : (A,B) slab of 4 columns  (0 if no A/B output is wanted)
-                        // blockIdx.x >= ab_blocks : C slab of 8 columns
+    int ab_blocks;      // blockIdx.x <  ab_blocks : (A,B) slab of 8 columns  (0 if no A/B output is wanted)
+                        // blockIdx.x >= ab_blocks : C slab of 16 columns
 };
 
 __device__ __forceinline__ float sqrt_approx(float x)
 {
     float r;
-    asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));  // MUFU.SQRT, ~1 ulp: the whitecap tolerance is 1e-5 of the Jacobian scale
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));  // MUFU.SQRT, ~1 ulp: the whitecap tolerance is 1e-5 of the Jacobian scale
+    return r;
+}
+__device__ __forceinline__ float rsqrt_ftz(float x)  // argument >= 1 here: no denormal fix-up wanted
+{
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
 
-// 5 packed lines per CTA, two kinds of CTA in one launch:
-//   (A,B) CTA: the (A,B) pairs of 4 columns + the halo column b0 + 4 (so that hds[index + 1] of
+// 9 packed lines per CTA, two kinds of CTA in one launch:
+//   (A,B) CTA: the (A,B) pairs of W = 8 columns + the halo column b0 + W (so that hds[index + 1] of
 //              FFTMesh.cs:266 is on chip)  -> hds, normal, Jacobian, whitecap
-//   C CTA    : the C field of 8 columns, two columns per packed line (4 lines busy)  -> height
+//   C CTA    : the C field of 16 columns, two columns per packed line (8 lines busy)  -> height
 //
-// Thread <-> data: thread tid < 4T owns line c = tid & 3 and residue g = tid >> 2 of the line (T = N/16
-// residues), so a warp is 8 consecutive g x 4 columns.  With that mapping
-//   * the first-stage inputs {row g + T k} x {4 columns} are loaded from global memory straight into
-//     registers as 64-byte row segments (no staging copy, no transposition pass);
-//   * after the last stage a warp holds 8 consecutive rows x 4 columns of finished values in
-//     registers, which is exactly the shape of a coalesced store: normals, hds and the whitecap are
-//     computed from registers; only the (dx, dz) pairs go through shared memory once more, for the
-//     forward differences of the Jacobian (FFTMesh.cs:260-267).
-// Threads tid >= 4T (one more group of T) run the halo line.
+// Thread <-> data: thread tid < 8T owns line c = tid & 7 and residue g = tid >> 3 of the line (T = N/16
+// residues), so a warp is 4 consecutive rows x 8 columns.  With that mapping
+//   * the first-stage inputs {row g + T k} x {8 columns} are loaded from global memory straight into
+//     registers as 128-byte row segments of one contiguous slab (no staging copy, no transposition pass);
+//   * after the last stage a warp holds 4 consecutive rows x 8 columns of finished values in registers,
+//     which is the shape of a store of whole 32-byte sectors: hds 64 B, normal 96 B, whitecap 32 B per row.
+//     Normals, hds and the whitecap are computed from registers; only the (dx, dz) pairs go through shared
+//     memory once more, for the forward differences of the Jacobian (FFTMesh.cs:260-267), and the normals
+//     take a per-warp 384-byte staging hop to leave as 16-byte stores.
+// Threads tid >= 8T (one more group of T) run the halo line.
+#ifndef MW_COLS_MAXREG
+#define MW_COLS_MAXREG 128
+#endif
 template <int N, int MINB>
-__global__ void __launch_bounds__(5 * (N / 16), MINB) k_cols_extract(const ColArgs a)
+__global__ void __launch_bounds__((slab_w(N) + 1) * (N / 16), MINB) __maxnreg__(N == 1024 ? MW_COLS_MAXREG : 128) k_cols_extract(const ColArgs a)
 {
     using P = Plan<N>;
-    using F = mwfft::Final<N>;
     constexpr int T = P::T;
-    constexpr int W = 4;
+    constexpr int W = slab_w(N);
+    constexpr int LOGW = mwfft::ilog2(W);
+    constexpr int XAB_ROW = W + 1;
     constexpr int LP = mwfft::line_pitch(N, W);
     constexpr bool LINEAR = (T % 16 == 0);
     extern __shared__ float4 smem4[];
     float4* tw2 = smem4;
     float2* tw3 = reinterpret_cast<float2*>(smem4 + P::TW2_F4);
-    float4* lines = smem4 + P::TW_BYTES / 16;  // [5][LP]
+    float4* lines = smem4 + P::TW_BYTES / 16;                              // [W + 1][LP]
+    float* nstage = reinterpret_cast<float*>(lines + (W + 1) * LP);         // [warps][96] normals of 32/W rows x W columns
 
     const int tile = a.tile0 + blockIdx.y;
     const int xt = blockIdx.y;
     const int tid = threadIdx.x;
     const bool is_halo = tid >= W * T;
-    const int c = is_halo ? W : (tid & 3);
-    const int g = is_halo ? tid - W * T : (tid >> 2);
+    const int c = is_halo ? W : (tid & (W - 1));
+    const int g = is_halo ? tid - W * T : (tid >> LOGW);
     const size_t plane = (size_t)N * N;
     const size_t obase = (size_t)tile * plane;
     float4* line = lines + c * LP;
@@ -382,7 +406,7 @@ __global__ void __launch_bounds__(5 * (N / 16), MINB) k_cols_extract(const ColAr
     mwfft::cpk v[16];
     const bool is_ab = (int)blockIdx.x < a.ab_blocks;
     const bool want_white = a.whitecap != nullptr || a.jacobian != nullptr;
-    const int b0 = is_ab ? blockIdx.x * W : ((int)blockIdx.x - a.ab_blocks) * 8;
+    const int b0 = is_ab ? blockIdx.x * W : ((int)blockIdx.x - a.ab_blocks) * (2 * W);
     // a group without a live line (halo group of a C slab, of the last slab, or when no whitecap is wanted)
     // transforms zeros: same instruction stream for every thread, no divergent barrier
     const bool active = is_ab ? (!is_halo || (want_white && b0 + W < N)) : !is_halo;
@@ -392,21 +416,21 @@ __global__ void __launch_bounds__(5 * (N / 16), MINB) k_cols_extract(const ColAr
     // ---- first-stage inputs straight from global memory: line position p = g + T k holds intermediate row
     //      (p + N/2) mod N = g + T ((k + 8) mod 16)  (the (-1)^a of sigma); slab-major layout => contiguous ----
     if (is_ab) {
-        const float4* src = a.XAB + (size_t)xt * plane * 5 / 4 + ((size_t)blockIdx.x * N + g) * 5 + c;
+        const float4* src = a.XAB + (size_t)xt * xab_tile_elems(N) + ((size_t)blockIdx.x * N + g) * XAB_ROW + c;
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
             float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (active && !(a.dbg_flags & 4)) e = ldg_stream4(src + (size_t)(T * ((k + 8) & 15)) * 5);
+            if (active && !(a.dbg_flags & 4)) e = ldg_stream4(src + (size_t)(T * ((k + 8) & 15)) * XAB_ROW);
             v[k].re = make_float2(e.x, e.y);
             v[k].im = make_float2(e.z, e.w);
         }
     } else {
         // 16 contiguous bytes = columns b0 + 2c, b0 + 2c + 1 of one row: (re0, im0, re1, im1)
-        const float4* src = reinterpret_cast<const float4*>(a.XC + (size_t)xt * plane + ((size_t)(b0 >> 3) * N + g) * 8 + (active ? 2 * c : 0));
+        const float4* src = reinterpret_cast<const float4*>(a.XC + (size_t)xt * plane + ((size_t)(b0 / (2 * W)) * N + g) * (2 * W) + (active ? 2 * c : 0));
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
             float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (active) e = ldg_stream4(src + (size_t)(T * ((k + 8) & 15)) * 4);
+            if (active) e = ldg_stream4(src + (size_t)(T * ((k + 8) & 15)) * W);
             v[k].re = make_float2(e.x, e.z);
             v[k].im = make_float2(e.y, e.w);
         }
@@ -442,7 +466,7 @@ __global__ void __launch_bounds__(5 * (N / 16), MINB) k_cols_extract(const ColAr
     }
     __syncthreads();
     MW_STAMP(3);
-    if (T >= 32 && is_halo) return;  // whole warps: done (for T < 32 they share a warp with owners and stay for the shuffles)
+    if (T >= 32 && is_halo) return;  // whole warps: done (for T < 32 they share a warp with owners and stay for the warp syncs)
     {
         const bool own = !is_halo && !(a.dbg_flags & 1);  // halo threads run the same code with every memory access predicated off
         if (a.dbg_flags & 16) return;
@@ -450,23 +474,33 @@ __global__ void __launch_bounds__(5 * (N / 16), MINB) k_cols_extract(const ColAr
         const size_t o0 = obase + (size_t)g * N + b0 + c;
         const bool last_col = b0 + c == N - 1;
         const float2* De = reinterpret_cast<const float2*>(line + LP);  // east neighbour's line
+        const int lane = tid & 31;
+        float* wst = nstage + (tid >> 5) * 96;  // this warp's staging: 4 rows x 8 columns x 3 floats, row-major
 #pragma unroll
         for (int s = 0; s < 16; ++s) {
             const int ar = mwfft::final_idx<N>(g, s);
             const size_t o = o0 + (size_t)(ar - g) * N;
             const float dx = v[s].re.x, sx = v[s].re.y, dz = v[s].im.x, sz = v[s].im.y;
             // nor = normalize(up - n) = (sx, 1, sz) / |.|   (FFTMesh.cs:212, 218)
-            const float inv = rsqrtf(sx * sx + 1.0f + sz * sz);
+            const float inv = rsqrt_ftz(sx * sx + 1.0f + sz * sz);
             const float nx = sx * inv, nz = sz * inv;
             if (a.normal) {
-                // the 4 lanes of a row hold 12 consecutive floats: regroup them into three 16-byte stores
-                // (shuffles are executed by every lane of the warp, stores only by owners)
-                const float px = __shfl_down_sync(0xffffffffu, nx, 1), py = __shfl_down_sync(0xffffffffu, inv, 1),
-                            pz = __shfl_down_sync(0xffffffffu, nz, 1);
-                float4* dst = reinterpret_cast<float4*>(a.normal + 3 * (o - c)) + c;
-                if (own && c == 0) *dst = make_float4(nx, inv, nz, px);
-                else if (own && c == 1) *dst = make_float4(inv, nz, px, py);
-                else if (own && c == 2) *dst = make_float4(nz, px, py, pz);
+                // lane l = (row l >> 3, column l & 7) holds floats [3l, 3l+3) of the warp's 96-float block; lanes
+                // 0..23 then store it as 24 float4 (6 per row = 96 contiguous bytes of the output row)
+                __syncwarp();
+                wst[3 * lane + 0] = nx;
+                wst[3 * lane + 1] = inv;
+                wst[3 * lane + 2] = nz;
+                __syncwarp();
+                if (lane < 24 && !(a.dbg_flags & 1)) {
+                    constexpr int QR = 3 * W / 4;                              // float4 per output row of the slab
+                    const int rr = lane / QR, qq = lane - QR * rr;             // row of the warp, float4 within the row
+                    const float4 q = *reinterpret_cast<const float4*>(wst + 3 * W * rr + 4 * qq);
+                    // output row = the row lane rr * W works on: same slot s, g differs by rr - (lane >> LOGW)
+                    const size_t orow = o - c + (size_t)(rr - (lane >> LOGW)) * N;  // column b0 of that row
+                    if (T >= 32 || tid - lane + W * rr < W * T)                    // (small N: rows of halo lanes do not exist)
+                        reinterpret_cast<float4*>(a.normal + 3 * orow)[qq] = q;
+                }
             }
             if (a.disp && own) a.disp[o] = make_float2(dx, dz);  // hds (FFTMesh.cs:247)
             if (want_white && own) {
@@ -493,7 +527,6 @@ __global__ void __launch_bounds__(5 * (N / 16), MINB) k_cols_extract(const ColAr
         }
     }
     MW_STAMP(4);
-    (void)F::R;
 }
 
 // =============================================================================================
