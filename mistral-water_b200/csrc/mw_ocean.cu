@@ -46,7 +46,7 @@ struct mw_ocean {
     float2* ramp = nullptr;   // [2N]
     float* kd = nullptr;      // [N]
     float2* tw = nullptr;     // [N]
-    float4* XAB = nullptr;    // [tiles][N/8][N][9] intermediate, fields A and B + halo copies (18 B / point)
+    float4* XAB = nullptr;    // [tiles][N/8][N][8] intermediate, fields A and B (16 B / point)
     float2* XC = nullptr;     // [tiles][N/16][N][16] intermediate, field C (8 B / point); lives right behind XAB
     // scratch outputs (host-pointer mode, or inputs of k_mesh_outputs)
     float* s_height = nullptr; float2* s_disp = nullptr; float* s_normal = nullptr; float* s_white = nullptr;
@@ -164,8 +164,8 @@ extern "C" int mw_ocean_create(const mw_ocean_params* params, mw_ocean** out)
     if ((rc = ensure(&o->kd, (size_t)N))) return fail(rc);
     if ((rc = ensure(&o->tw, (size_t)N))) return fail(rc);
     {
-        // group size: keep one group's intermediate (26 B per point) around 32 MB
-        long long gt = (32ll << 20) / (long long)(o->n2 * 26);
+        // group size: keep one group's intermediate (24 B per point) around 32 MB
+        long long gt = (32ll << 20) / (long long)(o->n2 * 24);
         if (const char* e = getenv("MW_GROUP_TILES")) gt = atoll(e);
         if (gt < 1) gt = 1;
         if (gt > o->tiles) gt = o->tiles;
@@ -174,7 +174,7 @@ extern "C" int mw_ocean_create(const mw_ocean_params* params, mw_ocean** out)
         if (o->slots < 2) o->slots = 2;
         if (o->slots > 4) o->slots = 4;
         o->x_tiles = o->tiles <= o->group_tiles ? o->tiles : o->slots * o->group_tiles;
-        char* x = nullptr;  // one allocation: 18 + 8 B per grid point of x_tiles tiles
+        char* x = nullptr;  // one allocation: 16 + 8 B per grid point of x_tiles tiles
         const size_t xab_bytes = mwk::xab_tile_elems(o->N) * sizeof(float4) * o->x_tiles;
         if ((rc = ensure(&x, xab_bytes + o->n2 * o->x_tiles * 8))) return fail(rc);
         o->XAB = reinterpret_cast<float4*>(x);

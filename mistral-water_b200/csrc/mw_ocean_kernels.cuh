@@ -142,11 +142,12 @@ __global__ void k_evolve(const float4* __restrict__ spec, const float* __restric
 // Intermediate layout (ours to choose), SLAB-MAJOR so that what one pass-2 CTA reads is one contiguous
 // block of memory (a row-major intermediate makes pass 2 read 64-byte pieces 16 KB apart, which runs the
 // HBM at a fraction of its bandwidth -- measured):
-//   XAB[tile][b / 8][n][9]   : float4 (A.re, B.re, A.im, B.im), A = chop-displacement field, B = slope field;
-//                              entries 0..7 = columns 8s..8s+7 of row n, entry 8 = a copy of column 8s+8
-//                              (the halo the Jacobian's forward difference needs)      18 B per grid point
+//   XAB[tile][b / 8][n][8]   : float4 (A.re, B.re, A.im, B.im), A = chop-displacement field, B = slope field
+//                              (columns 8s..8s+7 of row n: one 128-byte line)          16 B per grid point
 //   XC [tile][b / 16][n][16] : float2 (C.re, C.im), C = height field                     8 B per grid point
-// Pass 1 therefore scatters 128-byte pieces (writes: they are merged in the 126 MB L2 before they reach HBM).
+// Pass 1 therefore scatters whole 128-byte lines (writes: merged in the 126 MB L2 before they reach HBM).  The
+// halo column a pass-2 CTA needs (column 8s+8, for the Jacobian's forward difference) is read from the next slab:
+// a 16-byte read out of every 128-byte row there -- reads tolerate that, writes of partial sectors do not.
 // Slabs are 8 (16) columns wide because pass 2 must WRITE its outputs in rows of that many columns: measured
 // (tools/ubench/store_pattern.cu), 4-column output rows leave half-filled 32-byte sectors (whitecap 16 B,
 // normal 48 B per row) and the same bytes take 224 us instead of 71 us (8 columns) per 16 tiles.
@@ -154,20 +155,20 @@ __global__ void k_evolve(const float4* __restrict__ spec, const float* __restric
 __host__ __device__ constexpr int slab_w(int N) { return N <= 1024 ? 8 : 4; }
 __host__ __device__ constexpr size_t xab_index(int N, int n, int b)
 {
-    return ((size_t)(b / slab_w(N)) * N + n) * (slab_w(N) + 1) + (b % slab_w(N));
+    return ((size_t)(b / slab_w(N)) * N + n) * slab_w(N) + (b % slab_w(N));
 }
 __host__ __device__ constexpr size_t xc_index(int N, int n, int b)
 {
     return ((size_t)(b / (2 * slab_w(N))) * N + n) * (2 * slab_w(N)) + (b % (2 * slab_w(N)));
 }
-__host__ __device__ constexpr size_t xab_tile_elems(int N) { return (size_t)(N / slab_w(N)) * N * (slab_w(N) + 1); }
+__host__ __device__ constexpr size_t xab_tile_elems(int N) { return (size_t)N * N; }
 struct RowArgs {
     const float4* spec;    // [tiles][N][N]  (h0, h0conj)
     const float* omega;    // [N][N]
     const float2* ramp;    // [2N]  exp(i pi s (1-N)/N), s = n + m
     const float* kd;       // [N]   2 pi (i - N/2) / L, fp32 as FFTMesh.cs:201
     const float2* tw;      // [N]   exp(+2 pi i x / N)
-    float4* XAB;           // [tiles][N/8][N][9]
+    float4* XAB;           // [tiles][N/8][N][8]
     float2* XC;            // [tiles][N/16][N][16]
     float t;
     int tile0;             // first tile of this launch (blockIdx.y counts from it); X is indexed by blockIdx.y
@@ -304,9 +305,7 @@ __global__ void __launch_bounds__(RP * 3 * (N / 16), MINB) k_spectrum_rows(const
             for (int sl = 0; sl < 16; ++sl) {
                 const int idx = mwfft::final_idx<N>(g, sl);
                 const float4 e = make_float4(v[sl].re.x, v[sl].re.y, v[sl].im.x, v[sl].im.y);
-                const size_t at = xab_index(N, row, idx);
-                dst[at] = e;
-                if ((idx % slab_w(N)) == 0 && idx != 0) dst[at - (size_t)N * (slab_w(N) + 1) + slab_w(N)] = e;  // halo copy for the slab to the west
+                dst[xab_index(N, row, idx)] = e;
             }
         } else {
             float2* dst = a.XC + (size_t)xt * N * N;
@@ -325,7 +324,7 @@ __global__ void __launch_bounds__(RP * 3 * (N / 16), MINB) k_spectrum_rows(const
 // pass 2: column FFT + extraction (+ Jacobian whitecap)
 // =============================================================================================
 struct ColArgs {
-    const float4* XAB;  // [tiles][N/8][N][9]
+    const float4* XAB;  // [tiles][N/8][N][8]
     const float2* XC;   // [tiles][N/16][N][16]
     const float2* tw;   // [N]
     float* height;      // [tiles][N*N]     or NULL
@@ -378,7 +377,6 @@ __global__ void __launch_bounds__((slab_w(N) + 1) * (N / 16), MINB) __maxnreg__(
     constexpr int T = P::T;
     constexpr int W = slab_w(N);
     constexpr int LOGW = mwfft::ilog2(W);
-    constexpr int XAB_ROW = W + 1;
     constexpr int LP = mwfft::line_pitch(N, W);
     constexpr bool LINEAR = (T % 16 == 0);
     extern __shared__ float4 smem4[];
@@ -416,11 +414,13 @@ __global__ void __launch_bounds__((slab_w(N) + 1) * (N / 16), MINB) __maxnreg__(
     // ---- first-stage inputs straight from global memory: line position p = g + T k holds intermediate row
     //      (p + N/2) mod N = g + T ((k + 8) mod 16)  (the (-1)^a of sigma); slab-major layout => contiguous ----
     if (is_ab) {
-        const float4* src = a.XAB + (size_t)xt * xab_tile_elems(N) + ((size_t)blockIdx.x * N + g) * XAB_ROW + c;
+        // (the halo group, c == W, reads entry 0 of the same row of the next slab, N * W elements further on)
+        const float4* src = a.XAB + (size_t)xt * xab_tile_elems(N) + ((size_t)blockIdx.x * N + g) * W +
+                            (is_halo ? (size_t)N * W : (size_t)c);
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
             float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (active && !(a.dbg_flags & 4)) e = ldg_stream4(src + (size_t)(T * ((k + 8) & 15)) * XAB_ROW);
+            if (active && !(a.dbg_flags & 4)) e = ldg_stream4(src + (size_t)(T * ((k + 8) & 15)) * W);
             v[k].re = make_float2(e.x, e.y);
             v[k].im = make_float2(e.z, e.w);
         }
