@@ -396,10 +396,8 @@ __global__ void __launch_bounds__((slab_w(N) + 1) * (N / 16), MINB) __maxnreg__(
     float4* line = lines + c * LP;
     auto cta_sync = [] { __syncthreads(); };
 
-    mwfft::load_twiddles<N, +1>(tw2, tw3, a.tw);
 #define MW_STAMP(i) do { if (a.dbg && tid == 0) a.dbg[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 8 + (i)] = clock64(); } while (0)
     MW_STAMP(0);
-    __syncthreads();  // twiddle tables visible
 
     mwfft::cpk v[16];
     const bool is_ab = (int)blockIdx.x < a.ab_blocks;
@@ -409,7 +407,10 @@ __global__ void __launch_bounds__((slab_w(N) + 1) * (N / 16), MINB) __maxnreg__(
     // transforms zeros: same instruction stream for every thread, no divergent barrier
     const bool active = is_ab ? (!is_halo || (want_white && b0 + W < N)) : !is_halo;
     if ((a.dbg_flags & 8) && !is_ab) return;
-    if (T >= 32 && !active) return;  // whole warps with nothing to transform: exited threads are not waited for by barriers
+    if (T >= 32 && !active) {  // whole warps with nothing to transform: help with the tables, then leave
+        mwfft::load_twiddles<N, +1>(tw2, tw3, a.tw);
+        return;                // (exited threads are not waited for by barriers)
+    }
 
     // ---- first-stage inputs straight from global memory: line position p = g + T k holds intermediate row
     //      (p + N/2) mod N = g + T ((k + 8) mod 16)  (the (-1)^a of sigma); slab-major layout => contiguous ----
@@ -435,6 +436,8 @@ __global__ void __launch_bounds__((slab_w(N) + 1) * (N / 16), MINB) __maxnreg__(
             v[k].im = make_float2(e.y, e.w);
         }
     }
+    // the twiddle tables are fetched while the slab loads above are in flight
+    mwfft::load_twiddles<N, +1>(tw2, tw3, a.tw);
     MW_STAMP(1);
     if (!(a.dbg_flags & 2)) mwfft::fft_line_inreg<N, +1>(v, line, g, tw2, tw3, cta_sync);  // one instance for both kinds
     MW_STAMP(2);
