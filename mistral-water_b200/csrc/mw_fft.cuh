@@ -199,6 +199,50 @@ __device__ __forceinline__ void load_twiddles(float4* tw2, float2* tw3, const fl
     }
 }
 
+// The same tables as a ready-made image in global memory (host-built once per handle, twiddle_image below): the
+// per-CTA fill is then a straight 16-byte copy by NT threads (compile-time trip count, no index arithmetic).
+template <int N, int NT>
+__device__ __forceinline__ void load_twiddle_image(float4* smem_tw, const float4* __restrict__ img)
+{
+    constexpr int F4 = Plan<N>::TW_BYTES / 16;
+#pragma unroll
+    for (int i = 0; i < (F4 + NT - 1) / NT; ++i) {
+        const int e = threadIdx.x + i * NT;
+        if (F4 % NT == 0 || e < F4) smem_tw[e] = __ldg(img + e);
+    }
+}
+// Host side: fills img (Plan<N>::TW_BYTES / 16 float4) with the layout load_twiddles produces.
+template <class F2>
+inline void twiddle_image_host(int n, int sign, float* img /* TW_BYTES / 4 floats */, F2 gtw /* gtw(x) -> (cos, sin)(2 pi x / n) */)
+{
+    const int r2 = n / 16 < 16 ? n / 16 : 16;
+    const int r3 = n / (16 * r2);
+    const int row = r2 / 2 + 1;                 // float4 per tw2 row
+    const int tw2_f4 = 16 * row;
+    const int tws2 = n / (16 * r2);
+    for (int i = 0; i < tw2_f4 * 4; ++i) img[i] = 0.f;
+    for (int k = 0; k < 16; ++k)
+        for (int r = 0; r < r2; ++r) {
+            float c, s;
+            gtw((r * k * tws2) % n, c, s);
+            img[(k * 2 * row + r) * 2 + 0] = c;
+            img[(k * 2 * row + r) * 2 + 1] = sign < 0 ? -s : s;
+        }
+    if (r3 > 1)
+        for (int i = 0; i < 16 * r2; ++i) {
+            float c, s;
+            gtw(i, c, s);
+            img[tw2_f4 * 4 + 2 * i + 0] = c;
+            img[tw2_f4 * 4 + 2 * i + 1] = sign < 0 ? -s : s;
+        }
+}
+inline int twiddle_image_bytes(int n)
+{
+    const int r2 = n / 16 < 16 ? n / 16 : 16;
+    const int r3 = n / (16 * r2);
+    return 16 * (r2 / 2 + 1) * 16 + (r3 > 1 ? 16 * r2 * 8 : 0);
+}
+
 __device__ __forceinline__ float2 cmul_s(float2 a, float2 b)
 {
     return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
@@ -374,6 +418,16 @@ __device__ __forceinline__ int final_idx(int g, int slot)
     const int j = g + b * (N / PTS);
     const int k = j & (F::S - 1);
     return (j - k) * F::R + k + bitrev(i, ilog2(F::R)) * F::S;
+}
+// final_idx<N>(g, slot) == g + final_off<N>(slot): the group index only enters additively, because a thread's
+// butterflies j = g + b T never reach the stage stride S (B T <= S for every plan) -- so every address derived from a
+// result index is "one base + compile-time offset".
+template <int N>
+__host__ __device__ constexpr int final_off(int slot)
+{
+    using F = Final<N>;
+    static_assert(F::B * (N / PTS) <= F::S, "j = g + b T must stay below the stage stride");
+    return (slot % F::B) * (N / PTS) + bitrev(slot / F::B, ilog2(F::R)) * F::S;
 }
 template <int N, int SIGN, class Sync>
 __device__ __forceinline__ void fft_line_inreg(cpk (&v)[PTS], float4* line, int g, const float4* tw2, const float2* tw3,

@@ -41,11 +41,16 @@ struct mw_ocean {
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
     // device state
-    float4* spec = nullptr;   // [tiles][N*N] (h0, h0conj)
+    float4* spec = nullptr;   // [tiles][N*N] (h0, h0conj) as given (get_h0 / evolve_spectrum)
+    float4* spec_r = nullptr; // [tiles][N*N] -(h0, h0conj) * ramp[n + m]: what the frame kernels read
     float* omega = nullptr;   // [N*N]
+    int* qidx = nullptr;      // [N*N] omega / w0 (integer)
+    float2* ptab = nullptr;   // [q_max + 1] per-frame (cos, sin)(omega_q t)
+    int q_entries = 0;
     float2* ramp = nullptr;   // [2N]
     float* kd = nullptr;      // [N]
     float2* tw = nullptr;     // [N]
+    float4* twimg = nullptr;  // shared-memory twiddle tables of the frame kernels, ready to copy (sign +1)
     float4* XAB = nullptr;    // [tiles][N/8][N][8] intermediate, fields A and B (16 B / point)
     float2* XC = nullptr;     // [tiles][N/16][N][16] intermediate, field C (8 B / point); lives right behind XAB
     // scratch outputs (host-pointer mode, or inputs of k_mesh_outputs)
@@ -159,10 +164,13 @@ extern "C" int mw_ocean_create(const mw_ocean_params* params, mw_ocean** out)
     }
     o->stream = o->own_stream;
     if ((rc = ensure(&o->spec, o->n2 * o->tiles))) return fail(rc);
+    if ((rc = ensure(&o->spec_r, o->n2 * o->tiles))) return fail(rc);
     if ((rc = ensure(&o->omega, o->n2))) return fail(rc);
+    if ((rc = ensure(&o->qidx, o->n2))) return fail(rc);
     if ((rc = ensure(&o->ramp, (size_t)2 * N))) return fail(rc);
     if ((rc = ensure(&o->kd, (size_t)N))) return fail(rc);
     if ((rc = ensure(&o->tw, (size_t)N))) return fail(rc);
+    if ((rc = ensure(&o->twimg, (size_t)mwfft::twiddle_image_bytes(N) / 16))) return fail(rc);
     {
         // group size: keep one group's intermediate (24 B per point) around 32 MB
         long long gt = (32ll << 20) / (long long)(o->n2 * 24);
@@ -203,17 +211,31 @@ extern "C" int mw_ocean_create(const mw_ocean_params* params, mw_ocean** out)
         volatile float num = two_pi * d;
         kd[i] = num / p.length;
     }
+    std::vector<float> twimg(mwfft::twiddle_image_bytes(N) / 4);
+    mwfft::twiddle_image_host(N, +1, twimg.data(), [&](int x, float& c, float& s) { c = tw[x].x; s = tw[x].y; });
     if (cudaMemcpy(o->tw, tw.data(), N * sizeof(float2), cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(o->twimg, twimg.data(), twimg.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess ||
         cudaMemcpy(o->ramp, ramp.data(), 2 * N * sizeof(float2), cudaMemcpyHostToDevice) != cudaSuccess ||
         cudaMemcpy(o->kd, kd.data(), N * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
         mw_set_error("table upload failed: %s", cudaGetErrorString(cudaGetLastError()));
         return fail(MW_E_CUDA);
     }
-    mwk::k_dispersion<<<(unsigned)((o->n2 + 255) / 256), 256, 0, o->stream>>>(o->omega, N, p.length);
+    mwk::k_dispersion<<<(unsigned)((o->n2 + 255) / 256), 256, 0, o->stream>>>(o->omega, o->qidx, N, p.length);
     g_mw_launches.fetch_add(1);
-    if (cudaStreamSynchronize(o->stream) != cudaSuccess) {
-        mw_set_error("k_dispersion failed: %s", cudaGetErrorString(cudaGetLastError()));
-        return fail(MW_E_CUDA);
+    {
+        // |k| is largest at grid point (0, 0), so qidx[0] is the largest multiple of w0 on the grid
+        int qmax = -1;
+        if (cudaMemcpyAsync(&qmax, o->qidx, sizeof(int), cudaMemcpyDeviceToHost, o->stream) != cudaSuccess ||
+            cudaStreamSynchronize(o->stream) != cudaSuccess) {
+            mw_set_error("k_dispersion failed: %s", cudaGetErrorString(cudaGetLastError()));
+            return fail(MW_E_CUDA);
+        }
+        if (qmax < 0 || qmax > (1 << 24)) {
+            mw_set_error("dispersion table would need %d entries (length %g, resolution %d): unsupported", qmax, p.length, N);
+            return fail(MW_E_INVALID_ARG);
+        }
+        o->q_entries = qmax + 1;
+        if ((rc = ensure(&o->ptab, (size_t)o->q_entries))) return fail(rc);
     }
     *out = o;
     return MW_OK;
@@ -225,7 +247,7 @@ extern "C" void mw_ocean_destroy(mw_ocean* o)
     cudaSetDevice(o->p.device);
     if (o->stream) cudaStreamSynchronize(o->stream);
     for (auto& e : o->ev_pool) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
-    void* ptrs[] = {o->spec, o->omega, o->ramp, o->kd, o->tw, o->XAB, o->s_height, o->s_disp, o->s_normal,
+    void* ptrs[] = {o->spec, o->spec_r, o->qidx, o->ptab, o->twimg, o->omega, o->ramp, o->kd, o->tw, o->XAB, o->s_height, o->s_disp, o->s_normal,
                     o->s_white, o->s_jac, o->s_vert, o->s_col, o->s_h};
     for (void* q : ptrs) if (q) cudaFree(q);
     for (int i = 0; i < 3; ++i) {
@@ -267,6 +289,8 @@ extern "C" int mw_ocean_init_spectrum(mw_ocean* o)
     mwk::k_init_spectrum<<<(unsigned)((total + 127) / 128), 128, 0, o->stream>>>(
         o->spec, o->N, o->tiles, o->p.length, o->p.amplitude, o->p.wind_x, o->p.wind_y, o->p.seed);
     MW_LAUNCH_CHECK();
+    mwk::k_ramp_spectrum<<<(unsigned)((total + 255) / 256), 256, 0, o->stream>>>(o->spec, o->ramp, o->spec_r, o->N, (int64_t)total);
+    MW_LAUNCH_CHECK();
     if (!o->device_ptrs) MW_CUDA(cudaStreamSynchronize(o->stream));
     o->have_h0 = true;
     return MW_OK;
@@ -287,6 +311,8 @@ extern "C" int mw_ocean_set_h0(mw_ocean* o, const float* h0, const float* h0conj
         d0 = stage; d1 = stage + total;
     }
     mwk::k_pack_h0<<<(unsigned)((total + 255) / 256), 256, 0, o->stream>>>(o->spec, d0, d1, (int64_t)total);
+    MW_LAUNCH_CHECK();
+    mwk::k_ramp_spectrum<<<(unsigned)((total + 255) / 256), 256, 0, o->stream>>>(o->spec, o->ramp, o->spec_r, o->N, (int64_t)total);
     MW_LAUNCH_CHECK();
     if (stage) MW_CUDA(cudaFreeAsync(stage, o->stream));
     if (!o->device_ptrs) MW_CUDA(cudaStreamSynchronize(o->stream));
@@ -383,17 +409,17 @@ static int launch_rows(mw_ocean* o, const mwk::RowArgs& a, int ntiles, cudaStrea
     return MW_OK;
 }
 
-template <int N, int MINB>
-static int launch_cols(mw_ocean* o, mwk::ColArgs a, int ntiles, cudaStream_t st)
+template <int N, int MINB, int OUTS>
+static int launch_cols_outs(mw_ocean* o, mwk::ColArgs a, int ntiles, cudaStream_t st)
 {
     constexpr int W = mwk::slab_w(N);
     constexpr int threads = (W + 1) * (N / 16);
     constexpr size_t smem = mwfft::Plan<N>::TW_BYTES + (size_t)(W + 1) * mwfft::line_pitch(N, W) * sizeof(float4) +
-                            (size_t)((threads + 31) / 32) * 96 * sizeof(float);
+                            (size_t)((threads + 31) / 32) * 96 * mwk::nstage_slots(N) * sizeof(float);
     static bool attr_done[64] = {};
     if (!attr_done[o->p.device]) {
-        MW_CUDA(cudaFuncSetAttribute(mwk::k_cols_extract<N, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        MW_CUDA(cudaFuncSetAttribute(mwk::k_cols_extract<N, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout,
+        MW_CUDA(cudaFuncSetAttribute(mwk::k_cols_extract<N, MINB, OUTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        MW_CUDA(cudaFuncSetAttribute(mwk::k_cols_extract<N, MINB, OUTS>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                      cudaSharedmemCarveoutMaxShared));
         attr_done[o->p.device] = true;
     }
@@ -403,9 +429,19 @@ static int launch_cols(mw_ocean* o, mwk::ColArgs a, int ntiles, cudaStream_t st)
     if (a.ab_blocks + c_blocks == 0) return MW_OK;
     dim3 grid(a.ab_blocks + c_blocks, ntiles);
     ProfScope ps(o, 1);
-    mwk::k_cols_extract<N, MINB><<<grid, threads, smem, st>>>(a);
+    mwk::k_cols_extract<N, MINB, OUTS><<<grid, threads, smem, st>>>(a);
     MW_LAUNCH_CHECK();
     return MW_OK;
+}
+
+template <int N, int MINB>
+static int launch_cols(mw_ocean* o, const mwk::ColArgs& a, int ntiles, cudaStream_t st)
+{
+    // the two output sets the reference's frame asks for get straight-line kernels; anything else decides at run time
+    const int outs = (a.disp ? 1 : 0) | (a.normal ? 2 : 0) | (a.whitecap ? 4 : 0) | (a.jacobian ? 8 : 0);
+    if (outs == 7) return launch_cols_outs<N, MINB, 7>(o, a, ntiles, st);   // hds + normal + whitecap (EvaluateWaves)
+    if (outs == 3) return launch_cols_outs<N, MINB, 3>(o, a, ntiles, st);   // hds + normal
+    return launch_cols_outs<N, MINB, -1>(o, a, ntiles, st);
 }
 
 template <int N, int RP, int RMINB, int CMINB>
@@ -496,8 +532,11 @@ extern "C" int mw_ocean_generate(mw_ocean* o, float t, const mw_ocean_out* out)
         else { if ((rc = ensure(&o->s_jac, total))) return rc; d_jac = o->s_jac; }
     }
 
-    mwk::RowArgs ra{o->spec, o->omega, o->ramp, o->kd, o->tw, o->XAB, o->XC, t, 0, o->dbg_rows, o->dbg_flags};
-    mwk::ColArgs ca{o->XAB, o->XC, o->tw, d_height, d_disp, d_normal, d_white, d_jac, o->dbg_cols, o->dbg_flags, 0, 0};
+    // e^{i omega t} for every distinct omega of the grid (one entry per multiple of w0), then the frame
+    mwk::k_phase_table<<<(unsigned)((o->q_entries + 255) / 256), 256, 0, o->stream>>>(o->ptab, o->q_entries, o->p.length, t);
+    MW_LAUNCH_CHECK();
+    mwk::RowArgs ra{o->spec_r, o->qidx, o->ptab, o->kd, o->twimg, o->XAB, o->XC, 0, o->dbg_rows, o->dbg_flags};
+    mwk::ColArgs ca{o->XAB, o->XC, o->twimg, d_height, d_disp, d_normal, d_white, d_jac, o->dbg_cols, o->dbg_flags, 0, 0};
     if ((rc = run_frame(o, ra, ca))) return rc;
 
     float* d_vert = nullptr; float4* d_col = nullptr;

@@ -21,20 +21,42 @@ using mwfft::pad_idx;
 
 // Dispersion(n, m), FFTMesh.cs:141-147, bit-exact: every operation is the fp32 round-to-nearest
 // one the C# expression performs, in the same order, with no FMA contraction.
-__device__ __forceinline__ float dispersion_rn(int n, int m, int N, float length)
+// The quantisation makes omega an integer multiple q of w0 = 2 pi / L: omega = fl(q * w0).  q is kept next to omega
+// so that the per-frame e^{i omega t} can come from a table with one entry per q (k_phase_table) -- the entry is
+// computed from the same fp32 omega with the same fp32 product omega * t, so the values are the ones a per-point
+// evaluation gives, bit for bit.
+__device__ __forceinline__ float dispersion_w0(float length) { return __fdiv_rn(__fmul_rn(2.0f, MW_PI_F), length); }
+__device__ __forceinline__ float dispersion_q(int n, int m, int N, float length)
 {
-    const float w = __fdiv_rn(__fmul_rn(2.0f, MW_PI_F), length);
+    const float w = dispersion_w0(length);
     const float kx = __fdiv_rn(__fmul_rn(MW_PI_F, (float)(2 * n - N)), length);
     const float kz = __fdiv_rn(__fmul_rn(MW_PI_F, (float)(2 * m - N)), length);
     const float mag = __fsqrt_rn(__fadd_rn(__fmul_rn(kx, kx), __fmul_rn(kz, kz)));
-    return __fmul_rn(floorf(__fdiv_rn(__fsqrt_rn(__fmul_rn(MW_G_F, mag)), w)), w);
+    return floorf(__fdiv_rn(__fsqrt_rn(__fmul_rn(MW_G_F, mag)), w));
+}
+__device__ __forceinline__ float dispersion_rn(int n, int m, int N, float length)
+{
+    return __fmul_rn(dispersion_q(n, m, N, length), dispersion_w0(length));
 }
 
-__global__ void k_dispersion(float* __restrict__ omega, int N, float length)
+__global__ void k_dispersion(float* __restrict__ omega, int* __restrict__ qidx, int N, float length)
 {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= N * N) return;
-    omega[idx] = dispersion_rn(idx / N, idx % N, N, length);
+    const float q = dispersion_q(idx / N, idx % N, N, length);
+    omega[idx] = __fmul_rn(q, dispersion_w0(length));
+    qidx[idx] = (int)q;
+}
+
+// Per frame: ptab[q] = (cos, sin)(fl(fl(q * w0) * t)), FFTMesh.cs:183-185 for every distinct omega of the grid.
+__global__ void k_phase_table(float2* __restrict__ ptab, int entries, float length, float t)
+{
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= entries) return;
+    const float omegat = __fmul_rn(__fmul_rn((float)q, dispersion_w0(length)), t);
+    float sn, cs;
+    sincosf(omegat, &sn, &cs);
+    ptab[q] = make_float2(cs, sn);
 }
 
 // Phillips(n, m), FFTMesh.cs:149-166.  fp32 storage and operation order as in the source;
@@ -110,6 +132,21 @@ __global__ void k_unpack_h0(const float4* __restrict__ spec, float2* __restrict_
     h0c[i] = make_float2(s.z, s.w);
 }
 
+// What pass 1 reads every frame: -(h0, h0conj) * ramp[n + m].  The phase ramp r[n] r[m] and the constant sign of the
+// height field (C' = -H r r, see "Signs" below) are constant in time and commute with the evolution
+// h0 e^{iwt} + h0conj e^{-iwt}, so they are applied once here instead of once per point per frame.
+__global__ void k_ramp_spectrum(const float4* __restrict__ spec, const float2* __restrict__ ramp, float4* __restrict__ spec_r,
+                                int N, int64_t total)
+{
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= total) return;
+    const int idx = (int)(gid % ((int64_t)N * N));
+    const float2 r = ramp[idx / N + idx % N];
+    const float4 s = spec[gid];
+    const float2 a = cmul(make_float2(s.x, s.y), r), b = cmul(make_float2(s.z, s.w), r);
+    spec_r[gid] = make_float4(-a.x, -a.y, -b.x, -b.y);
+}
+
 // =============================================================================================
 // per-frame: h(k,t)
 // =============================================================================================
@@ -163,25 +200,17 @@ __host__ __device__ constexpr size_t xc_index(int N, int n, int b)
 }
 __host__ __device__ constexpr size_t xab_tile_elems(int N) { return (size_t)N * N; }
 struct RowArgs {
-    const float4* spec;    // [tiles][N][N]  (h0, h0conj)
-    const float* omega;    // [N][N]
-    const float2* ramp;    // [2N]  exp(i pi s (1-N)/N), s = n + m
+    const float4* spec;    // [tiles][N][N]  -(h0, h0conj) * ramp[n + m]   (k_ramp_spectrum)
+    const int* qidx;       // [N][N]  omega / w0  (k_dispersion)
+    const float2* ptab;    // [q_max + 1]  (cos, sin)(omega_q t) of this frame  (k_phase_table)
     const float* kd;       // [N]   2 pi (i - N/2) / L, fp32 as FFTMesh.cs:201
-    const float2* tw;      // [N]   exp(+2 pi i x / N)
+    const float4* twimg;   // shared-memory twiddle tables as a ready-made image (mwfft::twiddle_image_host)
     float4* XAB;           // [tiles][N/8][N][8]
     float2* XC;            // [tiles][N/16][N][16]
-    float t;
     int tile0;             // first tile of this launch (blockIdx.y counts from it); X is indexed by blockIdx.y
     long long* dbg;        // developer phase-timing buffer (NULL in production)
     int dbg_flags;         // developer experiments: 1 = no output stores, 2 = no FFT, 4 = no spectrum loads
 };
-
-// F[n,m] = (p1 * e1 - p2 * conj(e2)) * (-i/2): the Hermitian "imaginary part" packing of SURVEY 3.4
-__device__ __forceinline__ float2 herm_pack(float2 p1, float2 e1, float2 p2, float2 e2)
-{
-    const float2 d = csub(cmul(p1, e1), cmul(p2, cconj(e2)));
-    return make_float2(0.5f * d.y, -0.5f * d.x);
-}
 
 // Signs.  The direct sum equals sigma[a,b] * T[a,b] with sigma = -(-1)^(a+b), and Dz carries an
 // extra minus (FFTMesh.cs:215).  None of that costs an instruction here:
@@ -192,6 +221,19 @@ __device__ __forceinline__ float2 herm_pack(float2 p1, float2 e1, float2 p2, flo
 //       A' = -Im-part(ux Hc) + i Im-part(uz Hc)   => multiplier (-ux + i uz)
 //       B' = -Im-part(kx H)  - i Im-part(kz H)    => multiplier (-kx - i kz)
 //       C' = -H
+//
+// Hermitian "imaginary part" packing: with E = H r r at a grid point P, E~ = the same at the mirror
+// point -P and M the multiplier above,   F(P) = (-i/2) (M(P) E(P) - M(-P) conj(E(-P))).
+// The spectrum is stored as Eh = -E (k_ramp_spectrum), and M(-P) = -M(P) exactly (kd[N - i] == -kd[i] in fp32)
+// everywhere except where an index mirrors onto itself (rows / columns 0 and N/2), so for a general row pair
+//       F(P)  = Mh(P) (Eh(P) + conj(Eh(-P))),   F(-P) = -Mh(P) conj(Eh(P) + conj(Eh(-P))),   Mh = (i/2) M
+// -- one packed complex product serves both points of a mirror pair.  (Column 0 is self-mirrored too: general form.)
+
+// e^{i omega t} applied to the stored pair: a e + b conj(e)   (htilde, FFTMesh.cs:178-190)
+__device__ __forceinline__ float2 htilde_tab(float4 s, float2 e)
+{
+    return make_float2((s.x + s.z) * e.x - (s.y - s.w) * e.y, (s.x - s.z) * e.y + (s.y + s.w) * e.x);
+}
 
 // RP row pairs per CTA; 3 packed lines per pair: (A,B) of row rA, (A,B) of row rB, (C of rA, C of rB).
 template <int N, int RP, int MINB>
@@ -201,6 +243,7 @@ __global__ void __launch_bounds__(RP * 3 * (N / 16), MINB) k_spectrum_rows(const
     constexpr int T = P::T;
     constexpr int PAIR_THREADS = 3 * T;
     constexpr int LP = mwfft::line_pitch(N, 8);
+    constexpr int NIT = (N / 2 + 1 + PAIR_THREADS - 1) / PAIR_THREADS;  // tasks per thread (3)
     extern __shared__ float4 smem4[];
     float4* tw2 = smem4;
     float2* tw3 = reinterpret_cast<float2*>(smem4 + P::TW2_F4);
@@ -213,73 +256,118 @@ __global__ void __launch_bounds__(RP * 3 * (N / 16), MINB) k_spectrum_rows(const
     const int pair = blockIdx.x * RP + rp;  // < N/2
     float4* lines = all_lines + rp * 3 * LP;
 
-    mwfft::load_twiddles<N, +1>(tw2, tw3, a.tw);
 #define MW_RSTAMP(i) do { if (a.dbg && threadIdx.x == 0) a.dbg[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 8 + (i)] = clock64(); } while (0)
     MW_RSTAMP(0);
 
     const bool special = pair == 0;         // rows 0 and N/2 mirror onto themselves
     const int rA = special ? 0 : pair;
     const int rB = special ? N / 2 : N - pair;
-    const float4* spec = a.spec + (size_t)tile * N * N;
-    const float kxA = __ldg(a.kd + rA), kxB = __ldg(a.kd + rB);
+    const float4* specT = a.spec + (size_t)tile * N * N;   // CTA-uniform base; everything below is a 32-bit offset
+    const unsigned oA = (unsigned)rA * N, oB = (unsigned)rB * N;
 
     // ---- evolve + pack.  One task = the four grid points (rA|rB, m|m') with m' = -m mod N; the set is
-    //      closed under k -> -k, so every Hermitian partner is on hand and every point is read once. ----
+    //      closed under k -> -k, so every Hermitian partner is on hand and every point is read once.
+    //      All loads of a thread's (up to) three tasks are issued before the first use. ----
     if (a.dbg_flags & 512) return;
-#pragma unroll 1
-    for (int m = lt; m <= N / 2 && !(a.dbg_flags & 32); m += PAIR_THREADS) {
-        const int mm = (N - m) & (N - 1);
-        const float4 s1 = ldg_stream4(spec + rA * N + m);    // P1 = (rA, m)
-        const float4 s2 = ldg_stream4(spec + rB * N + mm);   // P2 = (rB, m')
-        const float4 s3 = ldg_stream4(spec + rA * N + mm);   // P3 = (rA, m')
-        const float4 s4 = ldg_stream4(spec + rB * N + m);    // P4 = (rB, m)
-        // omega depends on |k| only: general rows  w(P1) = w(P2), w(P3) = w(P4);
-        //                            special rows  w(P1) = w(P3), w(P4) = w(P2)
-        const float w1 = __ldg(a.omega + rA * N + m);
-        const float w2 = __ldg(a.omega + (special ? rB * N + m : rA * N + mm));
-        float sn1, cs1, sn2, cs2;
-        sincosf(__fmul_rn(w1, a.t), &sn1, &cs1);  // FFTMesh.cs:183
-        sincosf(__fmul_rn(w2, a.t), &sn2, &cs2);
-        const float2 E1 = cmul(htilde_eval(s1, cs1, sn1), __ldg(a.ramp + rA + m));
-        const float2 E2 = cmul(special ? htilde_eval(s2, cs2, sn2) : htilde_eval(s2, cs1, sn1), __ldg(a.ramp + rB + mm));
-        const float2 E3 = cmul(special ? htilde_eval(s3, cs1, sn1) : htilde_eval(s3, cs2, sn2), __ldg(a.ramp + rA + mm));
-        const float2 E4 = cmul(htilde_eval(s4, cs2, sn2), __ldg(a.ramp + rB + m));
-        const float kzm = __ldg(a.kd + m), kzmm = __ldg(a.kd + mm);
-        // |k| is shared inside a mirror pair; it differs between rows A and B only for the special pair
-        const float k2A = kxA * kxA + kzm * kzm, k2B = kxB * kxB + kzm * kzm;
-        const float invA = k2A < MW_EPSILON_F * MW_EPSILON_F ? 0.0f : rsqrtf(k2A);  // FFTMesh.cs:213-214
-        const float invB = k2B < MW_EPSILON_F * MW_EPSILON_F ? 0.0f : rsqrtf(k2B);
-        // packing multipliers with the output signs folded in (see "Signs" above), as packed pairs:
-        // lane x = the A' multiplier (-ux + i uz), lane y = the B' multiplier (-kx - i kz), so that one packed
-        // complex multiply serves both fields and the result IS the (A.re, B.re, A.im, B.im) line element
-        const float uxA = -kxA * invA, uxB = -kxB * invB;
-        const mwfft::cpk M1 = {make_float2(uxA, -kxA), make_float2(kzm * invA, -kzm)};    // P1 = (rA, m)
-        const mwfft::cpk M3 = {make_float2(uxA, -kxA), make_float2(kzmm * invA, -kzmm)};  // P3 = (rA, m')
-        const mwfft::cpk M2 = {make_float2(uxB, -kxB), make_float2(kzmm * invB, -kzmm)};  // P2 = (rB, m')
-        const mwfft::cpk M4 = {make_float2(uxB, -kxB), make_float2(kzm * invB, -kzm)};    // P4 = (rB, m)
-        // F = (M_self * E_self - M_partner * conj(E_partner)) * (-i/2)   (herm_pack, both lanes at once)
-        auto pack2 = [](const mwfft::cpk& ms, float2 es, const mwfft::cpk& mp, float2 ep) {
-            const mwfft::cpk d = mwfft::psub(mwfft::pmul(ms, es.x, es.y), mwfft::pmul(mp, ep.x, -ep.y));
-            const float2 h = make_float2(0.5f, 0.5f), nh = make_float2(-0.5f, -0.5f);
-            return make_float4(d.im.x * h.x, d.im.y * h.y, d.re.x * nh.x, d.re.y * nh.y);
-        };
-        float4 F1, F2, F3, F4;
-        if (!special) {  // partners: P1 <-> P2, P3 <-> P4
-            F1 = pack2(M1, E1, M2, E2); F2 = pack2(M2, E2, M1, E1);
-            F3 = pack2(M3, E3, M4, E4); F4 = pack2(M4, E4, M3, E3);
-        } else {         // partners: P1 <-> P3, P4 <-> P2
-            F1 = pack2(M1, E1, M3, E3); F3 = pack2(M3, E3, M1, E1);
-            F4 = pack2(M4, E4, M2, E2); F2 = pack2(M2, E2, M4, E4);
+    if (!(a.dbg_flags & 32)) {
+        float4 s1[NIT], s2[NIT], s3[NIT], s4[NIT];
+        int q1[NIT], q2[NIT];
+        float kz[NIT];
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+            const int m0 = lt + it * PAIR_THREADS;
+            const int m = m0 <= N / 2 ? m0 : N / 2;  // surplus threads: harmless repeat of the last task's loads
+            const int mm = (N - m) & (N - 1);
+            s1[it] = ldg_stream4(specT + (oA + m));    // P1 = (rA, m)
+            s2[it] = ldg_stream4(specT + (oB + mm));   // P2 = (rB, m')
+            s3[it] = ldg_stream4(specT + (oA + mm));   // P3 = (rA, m')
+            s4[it] = ldg_stream4(specT + (oB + m));    // P4 = (rB, m)
+            // omega depends on |k| only: general rows  w(P1) = w(P2), w(P3) = w(P4);
+            //                            special rows  w(P1) = w(P3), w(P4) = w(P2)
+            q1[it] = __ldg(a.qidx + (oA + m));
+            q2[it] = __ldg(a.qidx + (special ? oB + m : oA + mm));
+            kz[it] = __ldg(a.kd + m);
         }
-        // line positions shifted by N/2: the transform then carries the (-1)^b of sigma
-        const int pm = pad_idx((m + N / 2) & (N - 1)), pmm = pad_idx((mm + N / 2) & (N - 1));
-        // line 0 = (A,B) of row rA ; line 1 = (A,B) of row rB ; line 2 = (C of rA, C of rB)
-        lines[pm] = F1;
-        lines[pmm] = F3;
-        lines[LP + pm] = F4;
-        lines[LP + pmm] = F2;
-        lines[2 * LP + pm] = make_float4(-E1.x, -E4.x, -E1.y, -E4.y);
-        lines[2 * LP + pmm] = make_float4(-E3.x, -E2.x, -E3.y, -E2.y);
+        float2 e1[NIT], e2[NIT];
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+            e1[it] = __ldg(a.ptab + q1[it]);
+            e2[it] = __ldg(a.ptab + q2[it]);
+        }
+        // the twiddle tables are fetched while the spectrum loads are in flight
+        mwfft::load_twiddle_image<N, RP * PAIR_THREADS>(smem4, a.twimg);
+        const float kxA = __ldg(a.kd + rA), kxB = __ldg(a.kd + rB);
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+            const int m = lt + it * PAIR_THREADS;
+            if (m > N / 2) break;                       // (last iteration only)
+            const int mm = (N - m) & (N - 1);
+            const float kzm = kz[it];
+            const float kzmm = (m == 0) ? kzm : -kzm;   // kd[N - m] == -kd[m] exactly; kd[0] mirrors onto itself
+            // Eh = -(H r r) at the four points (the spectrum is stored ramped and negated)
+            const float2 E1 = htilde_tab(s1[it], e1[it]);
+            const float2 E2 = htilde_tab(s2[it], special ? e2[it] : e1[it]);
+            const float2 E3 = htilde_tab(s3[it], special ? e1[it] : e2[it]);
+            const float2 E4 = htilde_tab(s4[it], e2[it]);
+            // line positions shifted by N/2: the transform then carries the (-1)^b of sigma
+            const int pm = pad_idx((m + N / 2) & (N - 1)), pmm = pad_idx((mm + N / 2) & (N - 1));
+            float4 F1, F2, F3, F4;
+            if (!special && m != 0) {
+                // |k| is shared by the four points; Mh'' = -(i/2) M ... with Eh = -E:  F = Mh (Eh + conj(Eh~)),
+                // Mh(P) = (i/2)(-M(P))... written out: re = (-hz inv, hz), im = (-hx inv, -hx), hx = kx/2, hz = kz/2
+                // (lane x = the A' field, lane y = the B' field)
+                const float k2 = kxA * kxA + kzm * kzm;
+                const float inv = k2 < MW_EPSILON_F * MW_EPSILON_F ? 0.0f : rsqrtf(k2);  // FFTMesh.cs:213-214
+                const float hx = 0.5f * kxA, hz = 0.5f * kzm, hzz = 0.5f * kzmm;
+                const float2 are1 = make_float2(-hz * inv, hz), are3 = make_float2(-hzz * inv, hzz);
+                const float2 aim = make_float2(-hx * inv, -hx);
+                auto pack_pair = [](float2 are, float2 aim, float2 es, float2 ep, float4& Fs, float4& Fp) {
+                    const float x = es.x + ep.x, y = es.y - ep.y;      // S = Eh(P) + conj(Eh(-P))
+                    const float2 xx = make_float2(x, x), yy = make_float2(y, y);
+                    const float2 q = __fmul2_rn(aim, yy), u = __fmul2_rn(aim, xx);
+                    const float2 sre = __ffma2_rn(are, xx, mwfft::neg2(q));           // a x - b y
+                    const float2 sim = __ffma2_rn(are, yy, u);                        // a y + b x
+                    const float2 pre = __ffma2_rn(are, mwfft::neg2(xx), mwfft::neg2(q));  // -a x - b y
+                    const float2 pim = __ffma2_rn(are, yy, mwfft::neg2(u));           // a y - b x
+                    Fs = make_float4(sre.x, sre.y, sim.x, sim.y);
+                    Fp = make_float4(pre.x, pre.y, pim.x, pim.y);
+                };
+                pack_pair(are1, aim, E1, E2, F1, F2);   // P1 <-> P2
+                pack_pair(are3, aim, E3, E4, F3, F4);   // P3 <-> P4
+            } else {
+                // rows 0 and N/2 (partners P1 <-> P3 and P4 <-> P2) and column 0 of any row: the Nyquist index mirrors
+                // onto itself with the same kd, so M(-P) != -M(P) there and the packing is done in its general form
+                //   F = (i/2) (M_s Eh_s - M_p conj(Eh_p))
+                const float k2A = kxA * kxA + kzm * kzm, k2B = kxB * kxB + kzm * kzm;
+                const float invA = k2A < MW_EPSILON_F * MW_EPSILON_F ? 0.0f : rsqrtf(k2A);
+                const float invB = k2B < MW_EPSILON_F * MW_EPSILON_F ? 0.0f : rsqrtf(k2B);
+                const float uxA = -kxA * invA, uxB = -kxB * invB;
+                const mwfft::cpk M1 = {make_float2(uxA, -kxA), make_float2(kzm * invA, -kzm)};    // P1 = (rA, m)
+                const mwfft::cpk M3 = {make_float2(uxA, -kxA), make_float2(kzmm * invA, -kzmm)};  // P3 = (rA, m')
+                const mwfft::cpk M2 = {make_float2(uxB, -kxB), make_float2(kzmm * invB, -kzmm)};  // P2 = (rB, m')
+                const mwfft::cpk M4 = {make_float2(uxB, -kxB), make_float2(kzm * invB, -kzm)};    // P4 = (rB, m)
+                auto pack2 = [](const mwfft::cpk& ms, float2 es, const mwfft::cpk& mp, float2 ep) {
+                    const mwfft::cpk d = mwfft::psub(mwfft::pmul(ms, es.x, es.y), mwfft::pmul(mp, ep.x, -ep.y));
+                    return make_float4(-0.5f * d.im.x, -0.5f * d.im.y, 0.5f * d.re.x, 0.5f * d.re.y);
+                };
+                if (special) {
+                    F1 = pack2(M1, E1, M3, E3); F3 = pack2(M3, E3, M1, E1);
+                    F4 = pack2(M4, E4, M2, E2); F2 = pack2(M2, E2, M4, E4);
+                } else {
+                    F1 = pack2(M1, E1, M2, E2); F2 = pack2(M2, E2, M1, E1);
+                    F3 = pack2(M3, E3, M4, E4); F4 = pack2(M4, E4, M3, E3);
+                }
+            }
+            // line 0 = (A,B) of row rA ; line 1 = (A,B) of row rB ; line 2 = (C of rA, C of rB), C' = Eh
+            lines[pm] = F1;
+            lines[pmm] = F3;
+            lines[LP + pm] = F4;
+            lines[LP + pmm] = F2;
+            lines[2 * LP + pm] = make_float4(E1.x, E4.x, E1.y, E4.y);
+            lines[2 * LP + pmm] = make_float4(E3.x, E2.x, E3.y, E2.y);
+        }
+    } else {
+        mwfft::load_twiddle_image<N, RP * PAIR_THREADS>(smem4, a.twimg);
     }
     MW_RSTAMP(1);
     __syncthreads();
@@ -298,22 +386,40 @@ __global__ void __launch_bounds__(RP * 3 * (N / 16), MINB) k_spectrum_rows(const
         auto line_sync = [&] { mwfft::group_sync<T>(bar_id); };
         line_sync();  // everyone has read before anyone overwrites (in-place exchange)
         mwfft::fft_line_inreg<N, +1>(v, line, g, tw2, tw3, line_sync);
+        constexpr int W = slab_w(N);
         if (q < 2) {
             const int row = q ? rB : rA;
             float4* dst = a.XAB + (size_t)xt * xab_tile_elems(N);
+            if constexpr (T % W == 0) {
+                // result index = g + (multiple of T): slab and column-in-slab of g, then compile-time slab steps
+                const unsigned base = ((unsigned)(g / W) * N + row) * W + (g % W);
 #pragma unroll
-            for (int sl = 0; sl < 16; ++sl) {
-                const int idx = mwfft::final_idx<N>(g, sl);
-                const float4 e = make_float4(v[sl].re.x, v[sl].re.y, v[sl].im.x, v[sl].im.y);
-                dst[xab_index(N, row, idx)] = e;
+                for (int sl = 0; sl < 16; ++sl)
+                    dst[base + (unsigned)(mwfft::final_off<N>(sl) / W) * (N * W)] =
+                        make_float4(v[sl].re.x, v[sl].re.y, v[sl].im.x, v[sl].im.y);
+            } else {
+#pragma unroll
+                for (int sl = 0; sl < 16; ++sl)
+                    dst[xab_index(N, row, g + mwfft::final_off<N>(sl))] = make_float4(v[sl].re.x, v[sl].re.y, v[sl].im.x, v[sl].im.y);
             }
         } else {
             float2* dst = a.XC + (size_t)xt * N * N;
+            if constexpr (T % (2 * W) == 0) {
+                const unsigned base = ((unsigned)(g / (2 * W)) * N) * (2 * W) + (g % (2 * W));
+                const unsigned bA = base + (unsigned)rA * (2 * W), bB = base + (unsigned)rB * (2 * W);
 #pragma unroll
-            for (int sl = 0; sl < 16; ++sl) {
-                const int idx = mwfft::final_idx<N>(g, sl);
-                dst[xc_index(N, rA, idx)] = make_float2(v[sl].re.x, v[sl].im.x);
-                dst[xc_index(N, rB, idx)] = make_float2(v[sl].re.y, v[sl].im.y);
+                for (int sl = 0; sl < 16; ++sl) {
+                    const unsigned off = (unsigned)(mwfft::final_off<N>(sl) / (2 * W)) * (N * 2 * W);
+                    dst[bA + off] = make_float2(v[sl].re.x, v[sl].im.x);
+                    dst[bB + off] = make_float2(v[sl].re.y, v[sl].im.y);
+                }
+            } else {
+#pragma unroll
+                for (int sl = 0; sl < 16; ++sl) {
+                    const int idx = g + mwfft::final_off<N>(sl);
+                    dst[xc_index(N, rA, idx)] = make_float2(v[sl].re.x, v[sl].im.x);
+                    dst[xc_index(N, rB, idx)] = make_float2(v[sl].re.y, v[sl].im.y);
+                }
             }
         }
     }
@@ -326,7 +432,7 @@ __global__ void __launch_bounds__(RP * 3 * (N / 16), MINB) k_spectrum_rows(const
 struct ColArgs {
     const float4* XAB;  // [tiles][N/8][N][8]
     const float2* XC;   // [tiles][N/16][N][16]
-    const float2* tw;   // [N]
+    const float4* twimg;  // twiddle-table image
     float* height;      // [tiles][N*N]     or NULL
     float2* disp;       // [tiles][N*N]     or NULL   (hds)
     float* normal;      // [tiles][N*N][3]  or NULL
@@ -370,9 +476,13 @@ __device__ __forceinline__ float rsqrt_ftz(float x)  // argument >= 1 here: no d
 #ifndef MW_COLS_MAXREG
 #define MW_COLS_MAXREG 128
 #endif
-template <int N, int MINB>
+// OUTS: which (A,B)-slab outputs exist, as a compile-time set (bit 0 hds, 1 normal, 2 whitecap, 3 Jacobian) so that the
+// extraction is straight-line code; OUTS = -1 decides per pointer at run time (any other combination).
+__host__ __device__ constexpr int nstage_slots(int N) { return N >= 256 ? 4 : 1; }
+template <int N, int MINB, int OUTS>
 __global__ void __launch_bounds__((slab_w(N) + 1) * (N / 16), MINB) __maxnreg__(N == 1024 ? MW_COLS_MAXREG : 128) k_cols_extract(const ColArgs a)
 {
+    constexpr int NS = nstage_slots(N);
     using P = Plan<N>;
     constexpr int T = P::T;
     constexpr int W = slab_w(N);
@@ -383,7 +493,7 @@ __global__ void __launch_bounds__((slab_w(N) + 1) * (N / 16), MINB) __maxnreg__(
     float4* tw2 = smem4;
     float2* tw3 = reinterpret_cast<float2*>(smem4 + P::TW2_F4);
     float4* lines = smem4 + P::TW_BYTES / 16;                              // [W + 1][LP]
-    float* nstage = reinterpret_cast<float*>(lines + (W + 1) * LP);         // [warps][96] normals of 32/W rows x W columns
+    float* nstage = reinterpret_cast<float*>(lines + (W + 1) * LP);         // [warps][NS][96] normals of 32/W rows x W columns, NS slots
 
     const int tile = a.tile0 + blockIdx.y;
     const int xt = blockIdx.y;
@@ -401,14 +511,14 @@ __global__ void __launch_bounds__((slab_w(N) + 1) * (N / 16), MINB) __maxnreg__(
 
     mwfft::cpk v[16];
     const bool is_ab = (int)blockIdx.x < a.ab_blocks;
-    const bool want_white = a.whitecap != nullptr || a.jacobian != nullptr;
+    const bool want_white = OUTS < 0 ? (a.whitecap != nullptr || a.jacobian != nullptr) : (OUTS & 12) != 0;
     const int b0 = is_ab ? blockIdx.x * W : ((int)blockIdx.x - a.ab_blocks) * (2 * W);
     // a group without a live line (halo group of a C slab, of the last slab, or when no whitecap is wanted)
     // transforms zeros: same instruction stream for every thread, no divergent barrier
     const bool active = is_ab ? (!is_halo || (want_white && b0 + W < N)) : !is_halo;
     if ((a.dbg_flags & 8) && !is_ab) return;
     if (T >= 32 && !active) {  // whole warps with nothing to transform: help with the tables, then leave
-        mwfft::load_twiddles<N, +1>(tw2, tw3, a.tw);
+        mwfft::load_twiddle_image<N, (W + 1) * T>(smem4, a.twimg);
         return;                // (exited threads are not waited for by barriers)
     }
 
@@ -437,7 +547,7 @@ __global__ void __launch_bounds__((slab_w(N) + 1) * (N / 16), MINB) __maxnreg__(
         }
     }
     // the twiddle tables are fetched while the slab loads above are in flight
-    mwfft::load_twiddles<N, +1>(tw2, tw3, a.tw);
+    mwfft::load_twiddle_image<N, (W + 1) * T>(smem4, a.twimg);
     MW_STAMP(1);
     if (!(a.dbg_flags & 2)) mwfft::fft_line_inreg<N, +1>(v, line, g, tw2, tw3, cta_sync);  // one instance for both kinds
     MW_STAMP(2);
@@ -448,7 +558,7 @@ __global__ void __launch_bounds__((slab_w(N) + 1) * (N / 16), MINB) __maxnreg__(
             float* dst = a.height + obase + (size_t)g * N + b0 + 2 * c;
 #pragma unroll
             for (int s = 0; s < 16; ++s) {
-                const int ar = mwfft::final_idx<N>(g, s);
+                const int ar = g + mwfft::final_off<N>(s);
                 *reinterpret_cast<float2*>(dst + (size_t)(ar - g) * N) = v[s].re;
             }
         }
@@ -456,15 +566,30 @@ __global__ void __launch_bounds__((slab_w(N) + 1) * (N / 16), MINB) __maxnreg__(
     }
 
     // ------------------------------------------------------------------ (A, B) slab
-    // finished transform: lane x = dx + i dz, lane y = sx + i sz.  (dx, dz) to shared memory (in place of the
-    // line, 8 bytes per row) for the neighbours' forward differences.
+    // finished transform: lane x = dx + i dz, lane y = sx + i sz.  (dx, dz) / 2 go to shared memory (in place of the
+    // line, 8 bytes per row) for the neighbours' forward differences  0.5 (hds[idx] - hds[idx + N]),
+    // 0.5 (hds[idx] - hds[idx + 1])  (FFTMesh.cs:260-267).  The "no neighbour => derivative 0" edges (:260, :264)
+    // are data, not branches: row N (one past the end) holds a copy of row N - 1, and in the last slab the halo line
+    // holds a copy of column N - 1.
+    const bool has_disp = OUTS < 0 ? a.disp != nullptr : (OUTS & 1) != 0;
+    const bool has_normal = OUTS < 0 ? a.normal != nullptr : (OUTS & 2) != 0;
+    const bool has_white = OUTS < 0 ? a.whitecap != nullptr : (OUTS & 4) != 0;
+    const bool has_jac = OUTS < 0 ? a.jacobian != nullptr : (OUTS & 8) != 0;
+    const bool need_d = has_white || has_jac;
+    const bool last_slab = b0 + W >= N;  // CTA-uniform
     float2* D = reinterpret_cast<float2*>(line);
     const int pg = pad_idx(g);
-    if (want_white) {
+    auto dpos = [&](int s) { return LINEAR ? pg + mwfft::pad_step(mwfft::final_off<N>(s)) : pad_idx(g + mwfft::final_off<N>(s)); };
+    if (need_d) {
+        if (!(is_halo && last_slab)) {
 #pragma unroll
-        for (int s = 0; s < 16; ++s) {
-            const int ar = mwfft::final_idx<N>(g, s);
-            D[LINEAR ? pg + mwfft::pad_step(ar - g) : pad_idx(ar)] = make_float2(v[s].re.x, v[s].im.x);
+            for (int s = 0; s < 16; ++s) D[dpos(s)] = make_float2(0.5f * v[s].re.x, 0.5f * v[s].im.x);
+            if (g == T - 1) D[pad_idx(N)] = make_float2(0.5f * v[15].re.x, 0.5f * v[15].im.x);  // slot 15 is row g + N - T
+        }
+        if (last_slab && !is_halo && c == W - 1) {
+            float2* Dh = reinterpret_cast<float2*>(line + LP);
+#pragma unroll
+            for (int s = 0; s < 16; ++s) Dh[dpos(s)] = make_float2(0.5f * v[s].re.x, 0.5f * v[s].im.x);
         }
     }
     __syncthreads();
@@ -474,58 +599,67 @@ __global__ void __launch_bounds__((slab_w(N) + 1) * (N / 16), MINB) __maxnreg__(
         const bool own = !is_halo && !(a.dbg_flags & 1);  // halo threads run the same code with every memory access predicated off
         if (a.dbg_flags & 16) return;
         const int dn = pad_idx(g + 1) - pg;  // padded distance to the next row (1 or 2)
-        const size_t o0 = obase + (size_t)g * N + b0 + c;
-        const bool last_col = b0 + c == N - 1;
         const float2* De = reinterpret_cast<const float2*>(line + LP);  // east neighbour's line
         const int lane = tid & 31;
-        float* wst = nstage + (tid >> 5) * 96;  // this warp's staging: 4 rows x 8 columns x 3 floats, row-major
+        // per-thread output bases; a slot then adds a compile-time multiple of N
+        const size_t o0 = obase + (size_t)g * N + b0 + c;
+        float2* p_disp = has_disp ? a.disp + o0 : nullptr;
+        float* p_white = has_white ? a.whitecap + o0 : nullptr;
+        float* p_jac = has_jac ? a.jacobian + o0 : nullptr;
+        // normals leave as 16-byte stores: lane l = (row l >> LOGW, column l & (W-1)) puts (nx, ny, nz) at floats
+        // [3l, 3l+3) of the warp's 96-float block of a slot; lanes 0..23 then store the block as 24 float4
+        // (3W/4 per row = the slab's 12W contiguous bytes of an output row).  NS slots are staged per warp sync pair.
+        constexpr int QR = 3 * W / 4;
+        const int rr = lane / QR, qq = lane - QR * rr;  // row of the warp, float4 within the row
+        float* wst = nstage + (tid >> 5) * (96 * NS);
+        // column b0 of output row (first row of the warp + rr), as float4 index into the normal plane
+        float4* p_nrm = has_normal ? reinterpret_cast<float4*>(a.normal) + (3 * (obase + (size_t)(g - (lane >> LOGW) + rr) * N + b0)) / 4 + qq
+                                   : nullptr;
+        const bool nrm_lane = lane < 24 && !(a.dbg_flags & 1) && (T >= 32 || tid - lane + W * rr < W * T);  // (small N: rows of halo lanes do not exist)
 #pragma unroll
-        for (int s = 0; s < 16; ++s) {
-            const int ar = mwfft::final_idx<N>(g, s);
-            const size_t o = o0 + (size_t)(ar - g) * N;
-            const float dx = v[s].re.x, sx = v[s].re.y, dz = v[s].im.x, sz = v[s].im.y;
-            // nor = normalize(up - n) = (sx, 1, sz) / |.|   (FFTMesh.cs:212, 218)
-            const float inv = rsqrt_ftz(sx * sx + 1.0f + sz * sz);
-            const float nx = sx * inv, nz = sz * inv;
-            if (a.normal) {
-                // lane l = (row l >> 3, column l & 7) holds floats [3l, 3l+3) of the warp's 96-float block; lanes
-                // 0..23 then store it as 24 float4 (6 per row = 96 contiguous bytes of the output row)
-                __syncwarp();
-                wst[3 * lane + 0] = nx;
-                wst[3 * lane + 1] = inv;
-                wst[3 * lane + 2] = nz;
-                __syncwarp();
-                if (lane < 24 && !(a.dbg_flags & 1)) {
-                    constexpr int QR = 3 * W / 4;                              // float4 per output row of the slab
-                    const int rr = lane / QR, qq = lane - QR * rr;             // row of the warp, float4 within the row
-                    const float4 q = *reinterpret_cast<const float4*>(wst + 3 * W * rr + 4 * qq);
-                    // output row = the row lane rr * W works on: same slot s, g differs by rr - (lane >> LOGW)
-                    const size_t orow = o - c + (size_t)(rr - (lane >> LOGW)) * N;  // column b0 of that row
-                    if (T >= 32 || tid - lane + W * rr < W * T)                    // (small N: rows of halo lanes do not exist)
-                        reinterpret_cast<float4*>(a.normal + 3 * orow)[qq] = q;
+        for (int s0 = 0; s0 < 16; s0 += NS) {
+#pragma unroll
+            for (int j = 0; j < NS; ++j) {
+                const int s = s0 + j;
+                const int off = mwfft::final_off<N>(s);       // output row = g + off
+                const float dx = v[s].re.x, sx = v[s].re.y, dz = v[s].im.x, sz = v[s].im.y;
+                // nor = normalize(up - n) = (sx, 1, sz) / |.|   (FFTMesh.cs:212, 218)
+                const float r2 = fmaf(sx, sx, sz * sz);
+                const float inv = rsqrt_ftz(r2 + 1.0f);
+                const float nx = sx * inv, nz = sz * inv;
+                if (has_normal) {
+                    wst[96 * j + 3 * lane + 0] = nx;
+                    wst[96 * j + 3 * lane + 1] = inv;
+                    wst[96 * j + 3 * lane + 2] = nz;
+                }
+                if (has_disp && own) p_disp[(size_t)off * N] = make_float2(dx, dz);  // hds (FFTMesh.cs:247)
+                if (need_d) {
+                    const int pa = dpos(s);
+                    const float2 nbs = D[LINEAR ? pa + dn : pad_idx(g + off + 1)];  // hds[index + resolution] / 2  (:260-263)
+                    const float2 nbe = De[pa];                                       // hds[index + 1] / 2           (:264-267)
+                    const float hx = 0.5f * dx, hz = 0.5f * dz;
+                    const float ddx_x = hx - nbs.x, ddx_y = hz - nbs.y, ddy_x = hx - nbe.x, ddy_y = hz - nbe.y;
+                    const float jac = fmaf(1.0f + ddx_x, 1.0f + ddy_y, -(ddx_y * ddy_x));  // :268
+                    if (has_jac && own) p_jac[(size_t)off * N] = jac;
+                    if (has_white && own) {
+                        // noise = |(|n.x|, |n.z|) * 0.3| = 0.3 sqrt(sx^2 + sz^2) / |(sx, 1, sz)|   (:269-270)
+                        const float noise = 0.3f * inv * sqrt_approx(r2);
+                        float turb = fmaxf(1.0f - jac + noise, 0.0f);                           // :270
+                        turb = fminf(turb, 1.0f);                                               // SmoothStep clamps
+                        p_white[(size_t)off * N] = turb * turb * fmaf(-2.0f, turb, 3.0f);       // :273
+                    }
                 }
             }
-            if (a.disp && own) a.disp[o] = make_float2(dx, dz);  // hds (FFTMesh.cs:247)
-            if (want_white && own) {
-                const int pa = LINEAR ? pg + mwfft::pad_step(ar - g) : pad_idx(ar);
-                float2 dDdx = make_float2(0.f, 0.f), dDdy = make_float2(0.f, 0.f);
-                if (ar != N - 1) {  // hds[index + resolution]  (:260-263)
-                    const float2 nb = D[LINEAR ? pa + dn : pad_idx(ar + 1)];
-                    dDdx = make_float2(0.5f * (dx - nb.x), 0.5f * (dz - nb.y));
+            if (has_normal) {
+                __syncwarp();
+                if (nrm_lane) {
+#pragma unroll
+                    for (int j = 0; j < NS; ++j) {
+                        const float4 q = *reinterpret_cast<const float4*>(wst + 96 * j + 4 * lane);
+                        p_nrm[(3 * (size_t)mwfft::final_off<N>(s0 + j) * N) / 4] = q;
+                    }
                 }
-                if (!last_col) {  // hds[index + 1]  (:264-267)
-                    const float2 nb = De[pa];
-                    dDdy = make_float2(0.5f * (dx - nb.x), 0.5f * (dz - nb.y));
-                }
-                const float jac = (1.0f + dDdx.x) * (1.0f + dDdy.y) - dDdx.y * dDdy.x;  // :268
-                if (a.jacobian) a.jacobian[o] = jac;
-                if (a.whitecap) {
-                    // noise = |(|n.x|, |n.z|) * 0.3|   (:269-270)
-                    const float ax = fabsf(nx) * 0.3f, az = fabsf(nz) * 0.3f;
-                    float turb = fmaxf(1.0f - jac + sqrt_approx(ax * ax + az * az), 0.0f);  // :270
-                    turb = fminf(turb, 1.0f);                                          // SmoothStep clamps
-                    a.whitecap[o] = -2.0f * turb * turb * turb + 3.0f * turb * turb;   // :273
-                }
+                __syncwarp();
             }
         }
     }

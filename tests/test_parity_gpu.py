@@ -141,6 +141,27 @@ def test_full_sizes_vs_fp64_oracle(mw, cref, r64, N, t):
     _check_vs(out, ref, 1e-5, 1e-5, 1e-5 * jscale, normal_abs=1e-4)
 
 
+@pytest.mark.parametrize("N", [32, 64, 256, 1024, 2048])
+def test_self_mirrored_rows_and_columns(mw, r64, N):
+    """Rows / columns 0 and N/2 mirror onto themselves under k -> -k (kd[0] is the Nyquist value on both sides), so
+    the Hermitian packing takes its general form there.  With a Phillips spectrum those modes carry ~no energy at
+    large N and a mistake would hide below every tolerance: here ALL the energy sits on them (plus a few ordinary
+    modes so that both code paths meet in one frame)."""
+    rng = np.random.default_rng(N)
+    mask = np.zeros((N, N), bool)
+    mask[0, :] = mask[N // 2, :] = mask[:, 0] = mask[:, N // 2] = True
+    mask[rng.integers(0, N, 24), rng.integers(0, N, 24)] = True
+    h0 = (rng.standard_normal((N, N, 2)) * mask[..., None]).astype(np.float32).reshape(N * N, 2)
+    hc = (rng.standard_normal((N, N, 2)) * mask[..., None]).astype(np.float32).reshape(N * N, 2)
+    L = float(N)
+    ref = r64.evaluate_waves(h0, hc, N, L, 1.0, 1.0, 0.9)
+    with mw.Ocean(N) as o:
+        o.set_h0(h0, hc)
+        out = o.generate(0.9, names=("height", "disp", "normal", "jacobian"))
+    for k, rk in (("height", "height"), ("disp", "hds"), ("normal", "normals"), ("jacobian", "jacobian")):
+        assert rel_l2(out[k][0], ref[rk]) <= 1e-5, (k, rel_l2(out[k][0], ref[rk]))
+
+
 def test_config2_256_outputs_subset(mw, cref, r64):
     """Config 2 asks for height + displacement + normal only (no whitecap): other pointers NULL."""
     N = 256
