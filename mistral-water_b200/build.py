@@ -10,7 +10,9 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
-LIB = os.path.join(LIBDIR, "libmistral_ocean.so")
+# developer hook: MW_LIB_SUFFIX=_x MW_NVCC_DEFS="-DFOO=1" builds an experiment variant next to the product library
+SUFFIX = os.environ.get("MW_LIB_SUFFIX", "")
+LIB = os.path.join(LIBDIR, f"libmistral_ocean{SUFFIX}.so")
 SOURCES = ["mw_ocean.cu", "mw_fft2d.cu", "mw_gerstner.cu"]
 HEADERS = ["mw_common.cuh", "mw_fft.cuh", "mw_ocean_kernels.cuh", os.path.join("..", "..", "include", "mistral_ocean.h")]
 NVCC_FLAGS = [
@@ -35,7 +37,7 @@ def _stale(target: str, deps: list[str]) -> bool:
 
 def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(LIBDIR, exist_ok=True)
-    objdir = os.path.join(HERE, "build")
+    objdir = os.path.join(HERE, "build" + SUFFIX)
     os.makedirs(objdir, exist_ok=True)
     hdrs = [os.path.join(CSRC, h) for h in HEADERS] + [os.path.abspath(__file__)]
     nvcc = _nvcc()
@@ -44,7 +46,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         src = os.path.join(CSRC, s)
         obj = os.path.join(objdir, s.replace(".cu", ".o"))
         if force or _stale(obj, [src] + hdrs):
-            cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+            cmd = [nvcc] + NVCC_FLAGS + os.environ.get("MW_NVCC_DEFS", "").split() + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
             jobs.append(cmd)
 
     def run(cmd):

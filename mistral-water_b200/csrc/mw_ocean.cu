@@ -491,7 +491,8 @@ static int run_frame(mw_ocean* o, const mwk::RowArgs& ra, const mwk::ColArgs& ca
         case 512: return run_frame_n<512, 2, 2, 1>(o, ra, ca);
         case 1024: {
             static const int minb = getenv("MW_ROWS_MINB") ? atoi(getenv("MW_ROWS_MINB")) : 3;
-            return minb == 3 ? run_frame_n<1024, 1, 3, 1>(o, ra, ca) : run_frame_n<1024, 1, 4, 1>(o, ra, ca);
+            constexpr int CM = MW_SLABW_1024 == 4 ? 2 : 1;
+            return minb == 3 ? run_frame_n<1024, 1, 3, CM>(o, ra, ca) : run_frame_n<1024, 1, 4, CM>(o, ra, ca);
         }
         case 2048: return run_frame_n<2048, 1, 1, 1>(o, ra, ca);
     }

@@ -189,7 +189,10 @@ __global__ void k_evolve(const float4* __restrict__ spec, const float* __restric
 // (tools/ubench/store_pattern.cu), 4-column output rows leave half-filled 32-byte sectors (whitecap 16 B,
 // normal 48 B per row) and the same bytes take 224 us instead of 71 us (8 columns) per 16 tiles.
 // (N = 2048: 4-column slabs -- nine 2048-point packed lines do not fit in shared memory.)
-__host__ __device__ constexpr int slab_w(int N) { return N <= 1024 ? 8 : 4; }
+#ifndef MW_SLABW_1024
+#define MW_SLABW_1024 8
+#endif
+__host__ __device__ constexpr int slab_w(int N) { return N < 1024 ? 8 : (N == 1024 ? MW_SLABW_1024 : 4); }
 __host__ __device__ constexpr size_t xab_index(int N, int n, int b)
 {
     return ((size_t)(b / slab_w(N)) * N + n) * slab_w(N) + (b % slab_w(N));
@@ -480,7 +483,7 @@ __device__ __forceinline__ float rsqrt_ftz(float x)  // argument >= 1 here: no d
 // extraction is straight-line code; OUTS = -1 decides per pointer at run time (any other combination).
 __host__ __device__ constexpr int nstage_slots(int N) { return N >= 256 ? 4 : 1; }
 template <int N, int MINB, int OUTS>
-__global__ void __launch_bounds__((slab_w(N) + 1) * (N / 16), MINB) __maxnreg__(N == 1024 ? MW_COLS_MAXREG : 128) k_cols_extract(const ColArgs a)
+__global__ void __launch_bounds__((slab_w(N) + 1) * (N / 16), MINB) __maxnreg__(N == 1024 ? (MW_SLABW_1024 == 8 ? MW_COLS_MAXREG : 96) : 128) k_cols_extract(const ColArgs a)
 {
     constexpr int NS = nstage_slots(N);
     using P = Plan<N>;

@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libmistral_ocean.so")
+LIB_PATH = os.path.join(_HERE, "lib", f"libmistral_ocean{os.environ.get('MW_LIB_SUFFIX', '')}.so")  # suffix: developer experiment builds
 
 MW_OK = 0
 MW_E_INVALID_ARG = -1
