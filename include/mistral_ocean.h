@@ -49,7 +49,8 @@ enum {
 /* mw_ocean_params.flags */
 enum {
     MW_DEVICE_PTRS = 1u << 0, /* buffer arguments are device pointers; calls are stream-async   */
-    MW_PROFILE = 1u << 1      /* record CUDA events around each kernel (mw_ocean_kernel_times) */
+    MW_PROFILE = 1u << 1,     /* record CUDA events around each kernel (mw_ocean_kernel_times) */
+    MW_WRAP_REPEAT = 1u << 2  /* mw_renderer only: border taps wrap around instead of clamping       */
 };
 
 /*
@@ -157,6 +158,76 @@ int64_t mw_kernel_launch_count(void);
  * FFTMesh synthesis.  Always host pointers.
  */
 int mw_fft2d(int device, int32_t n, int32_t batch, int sign, const float* in, float* out);
+
+/*
+ * ---------------------------------------------------------------------------------------------
+ * OceanRenderer path: the GPU-shader convention the Ocean Demo scene runs (SURVEY.md section 8,
+ * rows a11-a13 + a10).  Replaces the blit chain of Scripts/OceanRenderer.cs GenerateTexture
+ * (:216-316) over Shaders/FFT/{InitialSpectrum, Dispersion, Spectrum, SpectrumHeight, Stockham,
+ * OceanNormal, WhiteCap}.shader.  It differs from the FFTMesh path in every convention (SURVEY.md
+ * section 3.5): FFT-ordered k, capillary dispersion with an accumulated phase, damping 0.01,
+ * amplitude / 10000, hash noise, forward-sign transform, choppiness inside the spectrum, stencil
+ * normals, +-8-texel Jacobian -- each restated from the shader it comes from.
+ *
+ * Images are R x R RGBAFloat, R = 8 * resolution (OceanRenderer.cs:136), row-major [y][x] with x
+ * (texcoord.x, the "horizontal" Stockham direction) contiguous: what Texture2D.LoadRawTextureData /
+ * GetRawTextureData use.  [tiles] images back to back.
+ */
+typedef struct mw_renderer_params {
+    int32_t resolution; /* OceanRenderer.cs:13  mesh resolution; textures are 8 x this (power of two, 4..256) */
+    float unit_width;   /* :12  (mesh only)                                                        */
+    float length;       /* :14  _Length                                                            */
+    float choppiness;   /* :16  _Choppiness (inside the spectrum, Spectrum.shader:48-49)           */
+    float amplitude;    /* :18  the shader receives amplitude / 10000 (:100, :149)                 */
+    float wind_x;       /* :19                                                                     */
+    float wind_y;
+    float mult;         /* :11  _DeltaTime = deltaTime * mult (:223)                               */
+    float seed1;        /* _RandomSeed1 = Random.value * 10 (:147); tile t uses seed + t           */
+    float seed2;        /* _RandomSeed2 (:148)                                                     */
+    int32_t device;
+    int32_t tiles;      /* independent oceans held by this handle (>= 1)                           */
+    uint32_t flags;     /* MW_DEVICE_PTRS | MW_WRAP_REPEAT                                         */
+    uint32_t reserved;
+} mw_renderer_params;
+
+/* The four maps OceanRenderer binds to the ocean material (OceanRenderer.cs:310-313). NULL = not requested. */
+typedef struct mw_renderer_out {
+    float* displacement; /* x4  _Anim   = (Re hx, Im hx, Re hz, Im hz)   displacementTexture (:244)           */
+    float* height;       /* x4  _Height = (Re h, Im h, Re h, Im h)       heightTexture (:280)                 */
+    float* normal;       /* x4  _Bump   = (n, 1)                         OceanNormal.shader:55                */
+    float* white;        /* x1  _White.r: the only channel ColorMask R lets through (WhiteCap.shader:14, :44) */
+    float* white_rgba;   /* x4  (xx, xx, xx, 1): the fragment's return value, for a plain RGBA upload         */
+    float* jacobian;     /* x1  the Jacobian before the smoothstep (WhiteCap.shader:38); test / debug output  */
+} mw_renderer_out;
+
+typedef struct mw_renderer mw_renderer; /* opaque */
+
+/* OceanRenderer.SetParams (:116-170): validates, allocates; the phase images start black (zero). */
+int mw_renderer_create(const mw_renderer_params* params, mw_renderer** out);
+void mw_renderer_destroy(mw_renderer* r);
+/* RenderInitial (:209-214): InitialSpectrum.shader on the device -> initialTexture. */
+int mw_renderer_render_initial(mw_renderer* r);
+/* initialTexture as data, [tiles][R*R] x4 = (h0, h0conj): upload the host's own (e.g. read back from Unity's
+ * GPU, whose hash noise depends on its sin) / read ours back.  With the phase image this is the whole state. */
+int mw_renderer_set_initial(mw_renderer* r, const float* rgba);
+int mw_renderer_get_initial(mw_renderer* r, float* rgba);
+/* the accumulated phase image (ping/pong RFloat textures, :60-61), [tiles][R*R] x1 */
+int mw_renderer_set_phase(mw_renderer* r, const float* phase);
+int mw_renderer_get_phase(mw_renderer* r, float* phase);
+/* OceanRenderer.Update's parameter refresh (:94-109): re-renders the initial spectrum when length, wind or
+ * amplitude changed. */
+int mw_renderer_set_params(mw_renderer* r, float length, float choppiness, float amplitude, float wind_x, float wind_y);
+/* GenerateTexture (:216-316): advances the phase by delta_time * mult and renders the requested maps. */
+int mw_renderer_generate_texture(mw_renderer* r, float delta_time, const mw_renderer_out* out);
+int mw_renderer_sync(mw_renderer* r);
+
+/*
+ * GenerateMesh (Scripts/OceanRenderer.cs:172-207; the same topology code is in Scripts/FFTMesh.cs:101-139):
+ * rest vertices [N*N] x3, normals (0,1,0) [N*N] x3, uvs [N*N] x2, triangle indices [(N-1)^2 * 6] in the
+ * reference's emission order.  Any pointer may be NULL.  Host pointers.
+ */
+int mw_mesh_generate(int device, int32_t resolution, float unit_width, float* vertices, float* normals, float* uvs,
+                     int32_t* indices);
 
 /*
  * Pond renderer: Gerstner sum-of-waves vertex displacement.

@@ -9,6 +9,7 @@
 // Why this equals the reference's O(N^4) direct sum: SURVEY.md section 3.4 / DESIGN.md.
 #pragma once
 #include "mw_fft.cuh"
+#include "mw_layout.cuh"
 
 namespace mwk {
 
@@ -189,19 +190,6 @@ __global__ void k_evolve(const float4* __restrict__ spec, const float* __restric
 // (tools/ubench/store_pattern.cu), 4-column output rows leave half-filled 32-byte sectors (whitecap 16 B,
 // normal 48 B per row) and the same bytes take 224 us instead of 71 us (8 columns) per 16 tiles.
 // (N = 2048: 4-column slabs -- nine 2048-point packed lines do not fit in shared memory.)
-#ifndef MW_SLABW_1024
-#define MW_SLABW_1024 8
-#endif
-__host__ __device__ constexpr int slab_w(int N) { return N < 1024 ? 8 : (N == 1024 ? MW_SLABW_1024 : 4); }
-__host__ __device__ constexpr size_t xab_index(int N, int n, int b)
-{
-    return ((size_t)(b / slab_w(N)) * N + n) * slab_w(N) + (b % slab_w(N));
-}
-__host__ __device__ constexpr size_t xc_index(int N, int n, int b)
-{
-    return ((size_t)(b / (2 * slab_w(N))) * N + n) * (2 * slab_w(N)) + (b % (2 * slab_w(N)));
-}
-__host__ __device__ constexpr size_t xab_tile_elems(int N) { return (size_t)N * N; }
 struct RowArgs {
     const float4* spec;    // [tiles][N][N]  -(h0, h0conj) * ramp[n + m]   (k_ramp_spectrum)
     const int* qidx;       // [N][N]  omega / w0  (k_dispersion)

@@ -18,6 +18,7 @@ MW_E_STATE = -4
 MW_E_NCCL = -5
 MW_DEVICE_PTRS = 1 << 0
 MW_PROFILE = 1 << 1
+MW_WRAP_REPEAT = 1 << 2
 MW_KERNEL_COUNT = 3
 MW_GERSTNER_MAX_WAVES = 64
 
@@ -28,7 +29,9 @@ EXPORTS = (
     "mw_ocean_evolve_spectrum", "mw_ocean_generate", "mw_ocean_update", "mw_ocean_reset_timer",
     "mw_ocean_timer", "mw_ocean_sync", "mw_ocean_set_stream", "mw_ocean_kernel_times",
     "mw_kernel_launch_count", "mw_fft2d", "mw_gerstner_from_material", "mw_gerstner_append_level_one",
-    "mw_gerstner_displace",
+    "mw_gerstner_displace", "mw_renderer_create", "mw_renderer_destroy", "mw_renderer_render_initial",
+    "mw_renderer_set_initial", "mw_renderer_get_initial", "mw_renderer_set_phase", "mw_renderer_get_phase",
+    "mw_renderer_set_params", "mw_renderer_generate_texture", "mw_renderer_sync", "mw_mesh_generate",
 )
 
 
@@ -50,6 +53,19 @@ class OceanParams(C.Structure):
 
 class OceanOut(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("height", "disp", "normal", "whitecap", "jacobian", "vertices", "colors")]
+
+
+class RendererParams(C.Structure):
+    _fields_ = [
+        ("resolution", C.c_int32), ("unit_width", C.c_float), ("length", C.c_float), ("choppiness", C.c_float),
+        ("amplitude", C.c_float), ("wind_x", C.c_float), ("wind_y", C.c_float), ("mult", C.c_float),
+        ("seed1", C.c_float), ("seed2", C.c_float), ("device", C.c_int32), ("tiles", C.c_int32), ("flags", C.c_uint32),
+        ("reserved", C.c_uint32),
+    ]
+
+
+class RendererOut(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("displacement", "height", "normal", "white", "white_rgba", "jacobian")]
 
 
 class GerstnerWave(C.Structure):
@@ -100,6 +116,18 @@ def load() -> C.CDLL:
                                               C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]
     lib.mw_gerstner_append_level_one.argtypes = [C.POINTER(GerstnerParams), C.c_float, C.c_float, C.c_float]
     lib.mw_gerstner_displace.argtypes = [C.POINTER(GerstnerParams), fp, fp, fp, C.c_int64, C.c_float, vp]
+    lib.mw_renderer_create.argtypes = [C.POINTER(RendererParams), C.POINTER(vp)]
+    lib.mw_renderer_destroy.argtypes = [vp]
+    lib.mw_renderer_destroy.restype = None
+    lib.mw_renderer_render_initial.argtypes = [vp]
+    lib.mw_renderer_set_initial.argtypes = [vp, fp]
+    lib.mw_renderer_get_initial.argtypes = [vp, fp]
+    lib.mw_renderer_set_phase.argtypes = [vp, fp]
+    lib.mw_renderer_get_phase.argtypes = [vp, fp]
+    lib.mw_renderer_set_params.argtypes = [vp, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float]
+    lib.mw_renderer_generate_texture.argtypes = [vp, C.c_float, C.POINTER(RendererOut)]
+    lib.mw_renderer_sync.argtypes = [vp]
+    lib.mw_mesh_generate.argtypes = [C.c_int, C.c_int32, C.c_float, fp, fp, fp, fp]
     _lib = lib
     return lib
 

@@ -44,8 +44,30 @@ def gerstner():
     print("gerstner_pond.npz", g4.shape)
 
 
+def renderer():
+    """OceanRenderer path, Ocean Demo scene values (Demo/Ocean Demo.unity:296-302) at mesh resolution 8 (R = 64):
+    the literal fp32 blit chain of oracle/ref_ocean_renderer.py after 3 frames of 16 ms."""
+    from oracle import ref_ocean_renderer as R
+    cfg = dict(resolution=8, length=434.48, choppiness=0.46, amplitude=0.41, wind=(14.45, 12.0), seed1=3.7, seed2=8.1, mult=1.5)
+    s = R.RendererState(cfg["resolution"], cfg["length"], cfg["choppiness"], cfg["amplitude"], cfg["wind"], cfg["seed1"],
+                        cfg["seed2"], cfg["mult"], np.float32)
+    out = {k: np.float32(v) if not isinstance(v, tuple) else np.array(v, np.float32) for k, v in cfg.items()}
+    out["resolution"] = np.int32(cfg["resolution"])
+    out.update(initial=s.initial.copy(), frames=np.int32(3), dt=np.float32(0.016))
+    for _ in range(3):
+        m = s.generate_texture(0.016)
+    for k in ("displacement", "height", "normal", "white", "jacobian", "phase"):
+        out[k] = m[k].astype(np.float32)
+    np.savez_compressed(os.path.join(HERE, "renderer_r64.npz"), **out)
+    print("renderer_r64.npz", {k: getattr(v, "shape", v) for k, v in out.items()})
+
+
 if __name__ == "__main__":
+    if "--renderer-only" in sys.argv:
+        renderer()
+        sys.exit(0)
     ocean(32, 1234, [0.0, 1.7, 60.0], "fftmesh_n32.npz")
     ocean(64, 1234, [1.7], "fftmesh_n64.npz")
     ocean(32, 99, [3.25], "fftmesh_n32_wind.npz", wind=(-2.0, 7.5), amplitude=0.0004, choppiness=0.46)
     gerstner()
+    renderer()
