@@ -270,6 +270,23 @@ int mw_gerstner_append_level_one(mw_gerstner_params* p, float amplitude, float f
 int mw_gerstner_displace(const mw_gerstner_params* p, const float* pos_xyz, float* out_xyz, float* out_nrm,
                          int64_t n, float t, void* cuda_stream);
 
+/*
+ * Pond renderer, `Wave` displacement mode (Shaders/MistralWaterLib.cginc Wave :127-152 through Displacement
+ * :160-164, keyword _DISPLACEMENTMODE_WAVE), for a mesh whose object and world frames coincide:
+ *   out_xyz[v] = (x, y + (y + A sin(s t + f x) - A cos(s t + f z)), z),  A = amplitude * 0.01
+ *   out_nrm[v] = normalize(cross(v2 - v0, v1 - v0)) of the two 0.05-offset neighbours after the _Smoothing blend.
+ */
+typedef struct mw_wave_params {
+    float amplitude; /* _Amplitude */
+    float frequency; /* _Frequency */
+    float speed;     /* _Speed     */
+    float smoothing; /* _Smoothing */
+    int32_t device;
+    uint32_t flags;  /* MW_DEVICE_PTRS */
+} mw_wave_params;
+int mw_wave_displace(const mw_wave_params* p, const float* pos_xyz, float* out_xyz, float* out_nrm, int64_t n, float t,
+                     void* cuda_stream);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

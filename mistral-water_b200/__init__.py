@@ -17,8 +17,8 @@ native.load()
 
 from .ocean import Ocean, fft2d  # noqa: E402
 from .fft_mesh import FFTMesh, Mesh  # noqa: E402
-from .pond import GerstnerWaves, POND_MATERIAL, pond_wave_table_32  # noqa: E402
+from .pond import GerstnerWaves, POND_MATERIAL, pond_wave_table_32, wave_displace  # noqa: E402
 from .ocean_renderer import OceanRenderer, Renderer, generate_mesh  # noqa: E402
 
 __all__ = ["native", "Ocean", "fft2d", "FFTMesh", "Mesh", "GerstnerWaves", "POND_MATERIAL", "pond_wave_table_32",
-           "OceanRenderer", "Renderer", "generate_mesh"]
+           "OceanRenderer", "Renderer", "generate_mesh", "wave_displace"]

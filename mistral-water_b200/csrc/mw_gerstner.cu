@@ -183,3 +183,83 @@ extern "C" int mw_gerstner_displace(const mw_gerstner_params* p, const float* po
     if (e != cudaSuccess) { mw_set_error("mw_gerstner_displace failed: %s", cudaGetErrorString(e)); return MW_E_CUDA; }
     return MW_OK;
 }
+
+
+// ---------------------------------------------------------------------------------------------
+// `Wave` displacement mode (MistralWaterLib.cginc:127-152 through Displacement :160-164)
+// ---------------------------------------------------------------------------------------------
+namespace {
+// sin / cos of speed + x * frequency: the phase is formed with the source's own fp32 roundings, reduced with a
+// three-term Cody-Waite step and evaluated on the MUFU unit (same scheme as k_gerstner)
+__device__ __forceinline__ void wave_sincos(float theta, float* s, float* c)
+{
+    const float k = rintf(theta * 0.15915494309189535f);
+    float r = fmaf(k, -6.28318548202514648f, theta);
+    r = fmaf(k, 1.74845553146e-7f, r);
+    r = fmaf(k, 1.2e-14f, r) ;
+    *s = __sinf(r);
+    *c = __cosf(r);
+}
+__global__ void __launch_bounds__(256) k_wave(const float* __restrict__ pos, float* __restrict__ out, float* __restrict__ nrm,
+                                              int64_t n, float speed, float amp, float frequency, float smoothing)
+{
+    const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n) return;
+    const float x = pos[3 * v], y = pos[3 * v + 1], z = pos[3 * v + 2];
+    float s0, c0, s1, c1, s2, c2, t;
+    wave_sincos(__fadd_rn(speed, __fmul_rn(x, frequency)), &s0, &t);
+    wave_sincos(__fadd_rn(speed, __fmul_rn(__fadd_rn(x, 0.05f), frequency)), &s1, &t);
+    wave_sincos(__fadd_rn(speed, __fmul_rn(z, frequency)), &t, &c0);
+    wave_sincos(__fadd_rn(speed, __fmul_rn(__fadd_rn(z, 0.05f), frequency)), &t, &c2);
+    s2 = s0;  // v2 shares x with v0 (:131), v1 shares z with v0 (:130)
+    c1 = c0;
+    const float y0 = y + s0 * amp - c0 * amp;
+    float y1 = y + s1 * amp - c1 * amp;
+    float y2 = y + s2 * amp - c2 * amp;
+    y1 -= (y1 - y0) * (1.0f - smoothing);  // :144-145
+    y2 -= (y2 - y0) * (1.0f - smoothing);
+    out[3 * v] = x;
+    out[3 * v + 1] = y + y0;               // v.vertex.y += offsets.y (:162), offsets = the displaced v0
+    out[3 * v + 2] = z;
+    if (nrm) {
+        // cross(v2 - v0, v1 - v0) with v2 - v0 = (0, y2 - y0, 0.05), v1 - v0 = (0.05, y1 - y0, 0)   (:147)
+        const float ax = 0.0f, ay = y2 - y0, az = __fsub_rn(__fadd_rn(z, 0.05f), z);
+        const float bx = __fsub_rn(__fadd_rn(x, 0.05f), x), by = y1 - y0, bz = 0.0f;
+        const float cx = ay * bz - az * by, cy = az * bx - ax * bz, cz = ax * by - ay * bx;
+        const float inv = rsqrtf(cx * cx + cy * cy + cz * cz);
+        nrm[3 * v] = cx * inv; nrm[3 * v + 1] = cy * inv; nrm[3 * v + 2] = cz * inv;
+    }
+}
+}  // namespace
+
+extern "C" int mw_wave_displace(const mw_wave_params* p, const float* pos_xyz, float* out_xyz, float* out_nrm, int64_t n,
+                                float t, void* cuda_stream)
+{
+    if (!p || !pos_xyz || !out_xyz || n < 0) { mw_set_error("mw_wave_displace: bad argument"); return MW_E_INVALID_ARG; }
+    if (n == 0) return MW_OK;
+    MW_CUDA(cudaSetDevice(p->device));
+    const bool dev = (p->flags & MW_DEVICE_PTRS) != 0;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const float* d_pos = pos_xyz;
+    float *d_out = out_xyz, *d_nrm = out_nrm, *scratch = nullptr;
+    const size_t bytes = (size_t)n * 3 * sizeof(float);
+    if (!dev) {
+        MW_CUDA(cudaMalloc((void**)&scratch, bytes * (out_nrm ? 3 : 2)));
+        d_pos = scratch; d_out = scratch + 3 * n; d_nrm = out_nrm ? scratch + 6 * n : nullptr;
+        cudaError_t e = cudaMemcpyAsync(scratch, pos_xyz, bytes, cudaMemcpyHostToDevice, st);
+        if (e != cudaSuccess) { cudaFree(scratch); mw_set_error("H2D failed: %s", cudaGetErrorString(e)); return MW_E_CUDA; }
+    }
+    volatile float speed = p->speed * t;          // :133
+    volatile float amp = p->amplitude * 0.01f;    // :134
+    k_wave<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_pos, d_out, d_nrm, n, speed, amp, p->frequency, p->smoothing);
+    g_mw_launches.fetch_add(1, std::memory_order_relaxed);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess && !dev) {
+        e = cudaMemcpyAsync(out_xyz, d_out, bytes, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess && out_nrm) e = cudaMemcpyAsync(out_nrm, d_nrm, bytes, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    }
+    if (scratch) cudaFree(scratch);
+    if (e != cudaSuccess) { mw_set_error("mw_wave_displace failed: %s", cudaGetErrorString(e)); return MW_E_CUDA; }
+    return MW_OK;
+}

@@ -31,7 +31,7 @@ EXPORTS = (
     "mw_kernel_launch_count", "mw_fft2d", "mw_gerstner_from_material", "mw_gerstner_append_level_one",
     "mw_gerstner_displace", "mw_renderer_create", "mw_renderer_destroy", "mw_renderer_render_initial",
     "mw_renderer_set_initial", "mw_renderer_get_initial", "mw_renderer_set_phase", "mw_renderer_get_phase",
-    "mw_renderer_set_params", "mw_renderer_generate_texture", "mw_renderer_sync", "mw_mesh_generate",
+    "mw_renderer_set_params", "mw_renderer_generate_texture", "mw_renderer_sync", "mw_mesh_generate", "mw_wave_displace",
 )
 
 
@@ -66,6 +66,11 @@ class RendererParams(C.Structure):
 
 class RendererOut(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("displacement", "height", "normal", "white", "white_rgba", "jacobian")]
+
+
+class WaveParams(C.Structure):
+    _fields_ = [("amplitude", C.c_float), ("frequency", C.c_float), ("speed", C.c_float), ("smoothing", C.c_float),
+                ("device", C.c_int32), ("flags", C.c_uint32)]
 
 
 class GerstnerWave(C.Structure):
@@ -128,6 +133,7 @@ def load() -> C.CDLL:
     lib.mw_renderer_generate_texture.argtypes = [vp, C.c_float, C.POINTER(RendererOut)]
     lib.mw_renderer_sync.argtypes = [vp]
     lib.mw_mesh_generate.argtypes = [C.c_int, C.c_int32, C.c_float, fp, fp, fp, fp]
+    lib.mw_wave_displace.argtypes = [C.POINTER(WaveParams), fp, fp, fp, C.c_int64, C.c_float, vp]
     _lib = lib
     return lib
 

@@ -87,3 +87,14 @@ def pond_wave_table_32(seed: int = 7, **kw) -> GerstnerWaves:
         f = m["_Frequency"] * fs
         g.append(d[0], d[1], f, sp * f, m["_Steepness"] * amp * st * a / 4.0, amp * a / 4.0)
     return g
+
+
+def wave_displace(pos, t, _Amplitude, _Frequency, _Speed, _Smoothing, want_normal=True, device=0):
+    """The `_DISPLACEMENTMODE_WAVE` branch of Displacement (MistralWaterLib.cginc:160-164 -> Wave :127-152) on host arrays:
+    returns (displaced vertices, normals)."""
+    pos = np.ascontiguousarray(pos, np.float32)
+    out = np.empty_like(pos)
+    nrm = np.empty_like(pos) if want_normal else None
+    p = native.WaveParams(float(_Amplitude), float(_Frequency), float(_Speed), float(_Smoothing), int(device), 0)
+    check(native.load().mw_wave_displace(C.byref(p), _addr(pos), _addr(out), _addr(nrm), pos.shape[0], float(t), None))
+    return out, nrm

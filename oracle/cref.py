@@ -49,6 +49,7 @@ def lib():
         _lib.ref_gerstner4.argtypes = [fp, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, fp, fp, fp, fp]
         _lib.ref_gerstner_level_one.argtypes = [fp, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, fp]
         _lib.ref_gerstner_table.argtypes = [fp, C.c_int, fp, C.c_int64, C.c_float, fp, fp]
+        _lib.ref_wave.argtypes = [fp, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, fp, fp]
     return _lib
 
 
@@ -168,3 +169,12 @@ def gerstner_table(waves, pos, t, want_normal=False):
     nrm = np.empty_like(pos) if want_normal else None
     lib().ref_gerstner_table(_p(waves), waves.shape[0], _p(pos), pos.shape[0], t, _p(out), _p(nrm))
     return (out, nrm) if want_normal else out
+
+
+def wave(pos, t, amplitude, frequency, speed, smoothing):
+    """MistralWaterLib.cginc:127-152 Wave through Displacement :160-164 -> (displaced vertices, normals)."""
+    pos = _f32(pos)
+    out = np.empty_like(pos)
+    nrm = np.empty_like(pos)
+    lib().ref_wave(_p(pos), pos.shape[0], t, amplitude, frequency, speed, smoothing, _p(out), _p(nrm))
+    return out, nrm

@@ -104,3 +104,35 @@ void ref_gerstner_table(const float* waves, int n_waves, const float* pos_xyz, i
         if (out_nrm) { out_nrm[3 * v + 0] = 0.f; out_nrm[3 * v + 1] = 1.f; out_nrm[3 * v + 2] = 0.f; }
     }
 }
+
+/* MistralWaterLib.cginc:127-152 Wave + its call site Displacement :160-164 (keyword _DISPLACEMENTMODE_WAVE), with
+ * unity_ObjectToWorld = unity_WorldToObject = identity (a pond mesh placed at the origin, unrotated, unscaled):
+ *   sVertex = worldPos = vertex;  out.y = vertex.y + offsets.y  where offsets = displaced v0 (so out.y = 2 y + wave);
+ *   normal = normalize(cross(v2 - v0, v1 - v0)) of the 0.05-offset neighbours after the _Smoothing blend. */
+void ref_wave(const float* pos_xyz, int64_t n, float time_y, float amplitude, float frequency, float s, float smoothing,
+              float* out_xyz, float* out_nrm)
+{
+    for (int64_t v = 0; v < n; ++v) {
+        float v0[3] = {pos_xyz[3 * v], pos_xyz[3 * v + 1], pos_xyz[3 * v + 2]};
+        float v1[3] = {v0[0] + 0.05f, v0[1], v0[2]};
+        float v2[3] = {v0[0], v0[1], v0[2] + 0.05f};
+        float speed = s * time_y;
+        float amp = amplitude * 0.01f;
+        v0[1] += fsin(speed + (v0[0] * frequency)) * amp;
+        v1[1] += fsin(speed + (v1[0] * frequency)) * amp;
+        v2[1] += fsin(speed + (v2[0] * frequency)) * amp;
+        v0[1] -= fcos(speed + (v0[2] * frequency)) * amp;
+        v1[1] -= fcos(speed + (v1[2] * frequency)) * amp;
+        v2[1] -= fcos(speed + (v2[2] * frequency)) * amp;
+        v1[1] -= (v1[1] - v0[1]) * (1.0f - smoothing);
+        v2[1] -= (v2[1] - v0[1]) * (1.0f - smoothing);
+        float a[3] = {v2[0] - v0[0], v2[1] - v0[1], v2[2] - v0[2]};
+        float b[3] = {v1[0] - v0[0], v1[1] - v0[1], v1[2] - v0[2]};
+        float c[3] = {a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]};
+        float len = (float)sqrt((double)(c[0] * c[0] + c[1] * c[1] + c[2] * c[2]));
+        out_xyz[3 * v + 0] = pos_xyz[3 * v];
+        out_xyz[3 * v + 1] = pos_xyz[3 * v + 1] + v0[1];   /* v.vertex.y += offsets.y (:162) */
+        out_xyz[3 * v + 2] = pos_xyz[3 * v + 2];
+        if (out_nrm) { out_nrm[3 * v] = c[0] / len; out_nrm[3 * v + 1] = c[1] / len; out_nrm[3 * v + 2] = c[2] / len; }
+    }
+}

@@ -92,3 +92,20 @@ def test_device_pointer_mode(mw, cref):
     torch.cuda.synchronize()
     ref = cref.gerstner_table(gw.table(), pos.cpu().numpy(), 0.9)
     assert np.abs(out.cpu().numpy() - ref).max() <= _tol(gw.table(), pos.cpu().numpy())
+
+
+@pytest.mark.parametrize("n", [1, 7, 1000, 65537])
+def test_wave_mode_matches_literal(mw, cref, n):
+    """`Wave` displacement (MistralWaterLib.cginc:127-152): vertices <= 2e-6 of the amplitude scale; normals <= 2e-3 --
+    they are built from 0.05-unit finite differences of fp32 heights, i.e. quotients of numbers at the rounding level of
+    the positions (|x| up to 500 here: ulp 6e-5 against a 0.05 step)."""
+    rng = np.random.default_rng(n)
+    pos = rng.uniform(-500, 500, (n, 3)).astype(np.float32)
+    pos[:, 1] = rng.uniform(-1, 1, n).astype(np.float32)
+    want, wn = cref.wave(pos, 12.5, 10.0, 2.58, 1.3, 0.4)
+    got, gn = mw.wave_displace(pos, 12.5, 10.0, 2.58, 1.3, 0.4)
+    assert np.abs(got - want).max() <= 2e-6 * 1.0 + 1e-6
+    assert np.array_equal(got[:, 0], pos[:, 0]) and np.array_equal(got[:, 2], pos[:, 2])
+    assert np.abs(gn - wn).max() <= 2e-3 and np.abs(np.linalg.norm(gn, axis=1) - 1).max() <= 1e-5
+    only, none = mw.wave_displace(pos, 12.5, 10.0, 2.58, 1.3, 0.4, want_normal=False)
+    assert none is None and np.array_equal(only, got)

@@ -153,8 +153,10 @@ def test_full_size_properties_2048(mw):
         n = m1["normal"][0, ..., :3].astype(np.float64)
         assert np.abs(np.linalg.norm(n, axis=-1) - 1).max() <= 1e-5
         assert m1["white"].min() >= 0.0 and m1["white"].max() <= 1.0
-        # the mean of the displacement image is the k = 0 mode = hx(0) = 0 (Phillips is 0 there)
-        assert abs(m1["height"][0, ..., 0].astype(np.float64).mean()) <= 1e-6 * float(np.abs(m1["height"]).max())
+        # the mean of the height image is the k = 0 input texel: h0 is 0 there (Phillips(0) = 0) but h0conj is not --
+        # InitialSpectrum.shader:47 evaluates it at index R - 1 (the mirror-index quirk) -- and its phase rate is 0
+        want_mean = float(ini[0, 0, 0, 0]) + float(ini[0, 0, 0, 2])
+        assert abs(m1["height"][0, ..., 0].astype(np.float64).mean() - want_mean) <= 1e-6 * float(np.abs(m1["height"]).max())
         # spot check a few texels of the height image against the direct DFT definition
         h0 = ini[0].astype(np.float64)
         phase = ph1[0].astype(np.float64)
