@@ -50,6 +50,35 @@ namespace MistralWater.Native
         [MarshalAs(UnmanagedType.ByValArray, SizeConst = 64)] public MwGerstnerWave[] waves;
     }
 
+    [StructLayout(LayoutKind.Sequential)]
+    public struct MwRendererParams         // mw_renderer_params: OceanRenderer's public fields (OceanRenderer.cs:10-19)
+    {
+        public int resolution;             // :13  mesh resolution; the maps are 8 x this
+        public float unitWidth;            // :12
+        public float length;               // :14
+        public float choppiness;           // :16
+        public float amplitude;            // :18  (the engine applies the / 10000 of :149)
+        public float windX, windY;         // :19
+        public float mult;                 // :11
+        public float seed1, seed2;         // Random.value * 10 (:147-148)
+        public int device, tiles;
+        public uint flags, reserved;       // MW_DEVICE_PTRS = 1, MW_WRAP_REPEAT = 4
+    }
+
+    [StructLayout(LayoutKind.Sequential)]
+    public struct MwRendererOut            // mw_renderer_out: IntPtr.Zero = not requested; R x R texels each
+    {
+        public IntPtr displacement;        // Color[]  -> _Anim    (OceanRenderer.cs:310)
+        public IntPtr height;              // Color[]  -> _Height  (:313)
+        public IntPtr normal;              // Color[]  -> _Bump    (:311)
+        public IntPtr white;               // float[]  -> _White.r (:312)
+        public IntPtr whiteRgba;           // Color[]  (xx, xx, xx, 1)
+        public IntPtr jacobian;            // float[]
+    }
+
+    [StructLayout(LayoutKind.Sequential)]
+    public struct MwWaveParams { public float amplitude, frequency, speed, smoothing; public int device; public uint flags; }
+
     public static class MistralOcean
     {
         const string Lib = "mistral_ocean";
@@ -82,7 +111,60 @@ namespace MistralWater.Native
         [DllImport(Lib)] public static extern int mw_gerstner_displace(ref MwGerstnerParams p, IntPtr posXyz, IntPtr outXyz, IntPtr outNrm,
             long n, float t, IntPtr cudaStream);
 
+        [DllImport(Lib)] public static extern int mw_renderer_create(ref MwRendererParams p, out IntPtr handle);
+        [DllImport(Lib)] public static extern void mw_renderer_destroy(IntPtr handle);
+        [DllImport(Lib)] public static extern int mw_renderer_render_initial(IntPtr handle);
+        [DllImport(Lib)] public static extern int mw_renderer_set_initial(IntPtr handle, IntPtr rgba);
+        [DllImport(Lib)] public static extern int mw_renderer_get_initial(IntPtr handle, IntPtr rgba);
+        [DllImport(Lib)] public static extern int mw_renderer_set_phase(IntPtr handle, IntPtr phase);
+        [DllImport(Lib)] public static extern int mw_renderer_get_phase(IntPtr handle, IntPtr phase);
+        [DllImport(Lib)] public static extern int mw_renderer_set_params(IntPtr handle, float length, float choppiness, float amplitude,
+            float windX, float windY);
+        [DllImport(Lib)] public static extern int mw_renderer_generate_texture(IntPtr handle, float deltaTime, ref MwRendererOut o);
+        [DllImport(Lib)] public static extern int mw_renderer_sync(IntPtr handle);
+        [DllImport(Lib)] public static extern int mw_mesh_generate(int device, int resolution, float unitWidth, IntPtr vertices,
+            IntPtr normals, IntPtr uvs, IntPtr indices);
+        [DllImport(Lib)] public static extern int mw_wave_displace(ref MwWaveParams p, IntPtr posXyz, IntPtr outXyz, IntPtr outNrm,
+            long n, float t, IntPtr cudaStream);
+
         public static void Check(int rc) { if (rc != MW_OK) throw new InvalidOperationException("mistral_ocean " + rc + ": " + LastError()); }
+    }
+
+    // The substitution inside OceanRenderer.cs (see INTEGRATION.md): the body of GenerateTexture.  The four maps go to
+    // Texture2D(R, R, TextureFormat.RGBAFloat / RFloat) objects with LoadRawTextureData(pinned array) + Apply(false),
+    // bound once to the ocean material exactly like the RenderTextures of :310-313.
+    public sealed class OceanRendererEngine : IDisposable
+    {
+        IntPtr handle;
+        GCHandle hd, hh, hn, hw;
+        MwRendererOut outBlock;
+        public readonly Color[] displacement, height, normal;
+        public readonly float[] white;
+
+        public OceanRendererEngine(int resolution, float unitWidth, float length, float choppiness, float amplitude, Vector2 wind, float mult)
+        {
+            var p = new MwRendererParams { resolution = resolution, unitWidth = unitWidth, length = length, choppiness = choppiness,
+                amplitude = amplitude, windX = wind.x, windY = wind.y, mult = mult, seed1 = UnityEngine.Random.value * 10f,
+                seed2 = UnityEngine.Random.value * 10f, device = 0, tiles = 1 };
+            MistralOcean.Check(MistralOcean.mw_renderer_create(ref p, out handle));   // OceanRenderer.cs:116-170
+            MistralOcean.Check(MistralOcean.mw_renderer_render_initial(handle));      // :209-214
+            int texels = 64 * resolution * resolution;
+            displacement = new Color[texels]; height = new Color[texels]; normal = new Color[texels]; white = new float[texels];
+            hd = GCHandle.Alloc(displacement, GCHandleType.Pinned); hh = GCHandle.Alloc(height, GCHandleType.Pinned);
+            hn = GCHandle.Alloc(normal, GCHandleType.Pinned); hw = GCHandle.Alloc(white, GCHandleType.Pinned);
+            outBlock = new MwRendererOut { displacement = hd.AddrOfPinnedObject(), height = hh.AddrOfPinnedObject(),
+                normal = hn.AddrOfPinnedObject(), white = hw.AddrOfPinnedObject() };
+        }
+
+        public void GenerateTexture(float deltaTime) { MistralOcean.Check(MistralOcean.mw_renderer_generate_texture(handle, deltaTime, ref outBlock)); }  // :216-316
+        public void SetParams(float length, float choppiness, float amplitude, Vector2 wind)                                                          // :94-109
+        { MistralOcean.Check(MistralOcean.mw_renderer_set_params(handle, length, choppiness, amplitude, wind.x, wind.y)); }
+
+        public void Dispose()
+        {
+            if (handle != IntPtr.Zero) { MistralOcean.mw_renderer_destroy(handle); handle = IntPtr.Zero; }
+            if (hd.IsAllocated) hd.Free(); if (hh.IsAllocated) hh.Free(); if (hn.IsAllocated) hn.Free(); if (hw.IsAllocated) hw.Free();
+        }
     }
 
     // The substitution inside FFTMesh.cs (see INTEGRATION.md): bodies of SetParams / GenerateMesh / EvaluateWaves.

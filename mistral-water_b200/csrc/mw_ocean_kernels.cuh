@@ -469,7 +469,10 @@ __device__ __forceinline__ float rsqrt_ftz(float x)  // argument >= 1 here: no d
 #endif
 // OUTS: which (A,B)-slab outputs exist, as a compile-time set (bit 0 hds, 1 normal, 2 whitecap, 3 Jacobian) so that the
 // extraction is straight-line code; OUTS = -1 decides per pointer at run time (any other combination).
-__host__ __device__ constexpr int nstage_slots(int N) { return N >= 256 ? 4 : 1; }
+#ifndef MW_NSTAGE
+#define MW_NSTAGE 4
+#endif
+__host__ __device__ constexpr int nstage_slots(int N) { return N >= 256 ? MW_NSTAGE : 1; }
 template <int N, int MINB, int OUTS>
 __global__ void __launch_bounds__((slab_w(N) + 1) * (N / 16), MINB) __maxnreg__(N == 1024 ? (MW_SLABW_1024 == 8 ? MW_COLS_MAXREG : 96) : 128) k_cols_extract(const ColArgs a)
 {

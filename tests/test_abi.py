@@ -36,6 +36,8 @@ def test_struct_layouts_match_header(mw):
     assert C.sizeof(n.OceanOut) == 7 * 8
     assert C.sizeof(n.GerstnerWave) == 24
     assert C.sizeof(n.GerstnerParams) == 16 + 64 * 24
+    assert C.sizeof(n.RendererParams) == 56 and n.RendererParams.seed1.offset == 32 and n.RendererParams.flags.offset == 48
+    assert C.sizeof(n.RendererOut) == 6 * 8 and C.sizeof(n.WaveParams) == 24
     fields = re.search(r"typedef struct mw_ocean_params \{(.*?)\} mw_ocean_params;", _header(), re.S).group(1)
     names = re.findall(r"\b(?:int32_t|uint32_t|uint64_t|float)\s+([a-z_0-9]+);", fields)
     assert names == [f[0] for f in n.OceanParams._fields_]
