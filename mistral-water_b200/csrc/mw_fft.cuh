@@ -24,7 +24,7 @@
 
 namespace mwfft {
 
-constexpr int PTS = 16;  // packed points per thread
+constexpr int PTS16 = 16;  // default packed points per thread (the PTS template parameter below: 16 or 32)
 
 // two complex numbers side by side: (re.x + i im.x) and (re.y + i im.y)
 struct cpk {
@@ -90,7 +90,7 @@ __device__ __forceinline__ cpk mul_w32(cpk d)
 
 // One decimation-in-frequency level over the R registers v[BASE + STRIDE * i], i < R.
 template <int SIGN, int LEN, int BASE, int STRIDE, int BLK, int K>
-__device__ __forceinline__ void dif_pair(cpk (&v)[PTS])
+__device__ __forceinline__ void dif_pair(cpk* v)
 {
     constexpr int i0 = BASE + STRIDE * (BLK + K);
     constexpr int i1 = BASE + STRIDE * (BLK + K + LEN / 2);
@@ -100,7 +100,7 @@ __device__ __forceinline__ void dif_pair(cpk (&v)[PTS])
 }
 template <int SIGN, int R, int LEN, int BASE, int STRIDE, int BLK, int K>
 struct DifK {
-    static __device__ __forceinline__ void run(cpk (&v)[PTS])
+    static __device__ __forceinline__ void run(cpk* v)
     {
         dif_pair<SIGN, LEN, BASE, STRIDE, BLK, K>(v);
         if constexpr (K + 1 < LEN / 2) DifK<SIGN, R, LEN, BASE, STRIDE, BLK, K + 1>::run(v);
@@ -108,7 +108,7 @@ struct DifK {
 };
 template <int SIGN, int R, int LEN, int BASE, int STRIDE, int BLK>
 struct DifBlk {
-    static __device__ __forceinline__ void run(cpk (&v)[PTS])
+    static __device__ __forceinline__ void run(cpk* v)
     {
         DifK<SIGN, R, LEN, BASE, STRIDE, BLK, 0>::run(v);
         if constexpr (BLK + LEN < R) DifBlk<SIGN, R, LEN, BASE, STRIDE, BLK + LEN>::run(v);
@@ -116,7 +116,7 @@ struct DifBlk {
 };
 template <int SIGN, int R, int LEN, int BASE, int STRIDE>
 struct DifLevel {
-    static __device__ __forceinline__ void run(cpk (&v)[PTS])
+    static __device__ __forceinline__ void run(cpk* v)
     {
         DifBlk<SIGN, R, LEN, BASE, STRIDE, 0>::run(v);
         if constexpr (LEN > 2) DifLevel<SIGN, R, LEN / 2, BASE, STRIDE>::run(v);
@@ -124,12 +124,12 @@ struct DifLevel {
 };
 // In-register radix-R DFT of v[BASE + STRIDE * i]; output X[bitrev(i)] is left in slot i.
 template <int SIGN, int R, int BASE, int STRIDE>
-__device__ __forceinline__ void dft_regs(cpk (&v)[PTS])
+__device__ __forceinline__ void dft_regs(cpk* v)
 {
     if constexpr (R >= 2) DifLevel<SIGN, R, R, BASE, STRIDE>::run(v);
 }
 template <int SIGN, int R, int B, int BASE = 0>
-__device__ __forceinline__ void dft_all(cpk (&v)[PTS])
+__device__ __forceinline__ void dft_all(cpk* v)
 {
     dft_regs<SIGN, R, BASE, B>(v);
     if constexpr (BASE + 1 < B) dft_all<SIGN, R, B, BASE + 1>(v);
@@ -143,20 +143,21 @@ __host__ __device__ constexpr int pad_idx(int i) { return i + (i >> 4); }
 // W-column slab (lane = column + W * row) touch 8 distinct 16-byte bank groups per quarter warp
 __host__ __device__ constexpr int line_pitch(int n, int w) { return ((n + n / 16 + 7) / 8) * 8 + 8 / w; }
 
-template <int N>
+template <int N, int PTS = PTS16>
 struct Plan {
     static_assert(N >= 32 && N <= 4096 && (N & (N - 1)) == 0, "N must be a power of two in [32, 4096]");
+    static_assert((PTS == 16 || PTS == 32) && N >= 2 * PTS, "16 or 32 packed points per thread");
     static constexpr int T = N / PTS;                           // threads per packed line
-    static constexpr int R1 = 16;                               // first radix
-    static constexpr int R2 = N / 16 < 16 ? N / 16 : 16;        // second radix
-    static constexpr int R3 = N / (16 * R2);                    // third radix (1 => two stages)
-    // twiddle tables kept in shared memory (filled once per CTA by load_twiddles):
-    //   tw2[k][r] = W_{16 R2}^{r k}, k < 16, r < R2: rows of R2 float2 (+ 16 B pad so that the LDS.128 of
+    static constexpr int R1 = PTS;                              // first radix: all of a thread's points in one butterfly
+    static constexpr int R2 = N / R1 < PTS ? N / R1 : PTS;      // second radix
+    static constexpr int R3 = N / (R1 * R2);                    // third radix (1 => two stages, ONE shared-memory exchange)
+    // twiddle tables kept in shared memory (filled once per CTA by load_twiddles / load_twiddle_image):
+    //   tw2[k][r] = W_{R1 R2}^{r k}, k < R1, r < R2: rows of R2 float2 (+ 16 B pad so that the LDS.128 of
     //               eight lanes with consecutive k are conflict free)
-    //   tw3[k]    = W_N^k, k < 16 R2 (third stage: the powers r = 2.. are formed by multiplication)
+    //   tw3[k]    = W_N^k, k < R1 R2 (third stage: the powers r = 2.. are formed by multiplication)
     static constexpr int TW2_ROW = R2 / 2 + 1;                  // float4 per row
-    static constexpr int TW2_F4 = 16 * TW2_ROW;
-    static constexpr int TW3_F2 = R3 > 1 ? 16 * R2 : 0;
+    static constexpr int TW2_F4 = R1 * TW2_ROW;
+    static constexpr int TW3_F2 = R3 > 1 ? R1 * R2 : 0;
     static constexpr int TW_BYTES = TW2_F4 * 16 + TW3_F2 * 8;
 };
 
@@ -178,20 +179,20 @@ __device__ __forceinline__ void group_sync(int line_id)
 
 // Fill the shared twiddle tables from the global table gtw[x] = exp(+2 pi i x / N) (SIGN < 0 conjugates).
 // Every thread of the CTA takes part; the caller's next __syncthreads publishes the tables.
-template <int N, int SIGN>
+template <int N, int SIGN, int PTS = PTS16>
 __device__ __forceinline__ void load_twiddles(float4* tw2, float2* tw3, const float2* __restrict__ gtw)
 {
-    using P = Plan<N>;
+    using P = Plan<N, PTS>;
     float2* t2 = reinterpret_cast<float2*>(tw2);
-    constexpr int TWS2 = N / (16 * P::R2);
-    for (int i = threadIdx.x; i < 16 * P::R2; i += blockDim.x) {
+    constexpr int TWS2 = N / (P::R1 * P::R2);
+    for (int i = threadIdx.x; i < P::R1 * P::R2; i += blockDim.x) {
         const int k = i / P::R2, r = i % P::R2;
         float2 w = __ldg(gtw + r * k * TWS2);
         if (SIGN < 0) w.y = -w.y;
         t2[k * (2 * P::TW2_ROW) + r] = w;
     }
     if constexpr (P::R3 > 1) {
-        for (int i = threadIdx.x; i < 16 * P::R2; i += blockDim.x) {
+        for (int i = threadIdx.x; i < P::R1 * P::R2; i += blockDim.x) {
             float2 w = __ldg(gtw + i);
             if (SIGN < 0) w.y = -w.y;
             tw3[i] = w;
@@ -201,10 +202,10 @@ __device__ __forceinline__ void load_twiddles(float4* tw2, float2* tw3, const fl
 
 // The same tables as a ready-made image in global memory (host-built once per handle, twiddle_image below): the
 // per-CTA fill is then a straight 16-byte copy by NT threads (compile-time trip count, no index arithmetic).
-template <int N, int NT>
+template <int N, int NT, int PTS = PTS16>
 __device__ __forceinline__ void load_twiddle_image(float4* smem_tw, const float4* __restrict__ img)
 {
-    constexpr int F4 = Plan<N>::TW_BYTES / 16;
+    constexpr int F4 = Plan<N, PTS>::TW_BYTES / 16;
 #pragma unroll
     for (int i = 0; i < (F4 + NT - 1) / NT; ++i) {
         const int e = threadIdx.x + i * NT;
@@ -213,15 +214,17 @@ __device__ __forceinline__ void load_twiddle_image(float4* smem_tw, const float4
 }
 // Host side: fills img (Plan<N>::TW_BYTES / 16 float4) with the layout load_twiddles produces.
 template <class F2>
-inline void twiddle_image_host(int n, int sign, float* img /* TW_BYTES / 4 floats */, F2 gtw /* gtw(x) -> (cos, sin)(2 pi x / n) */)
+inline void twiddle_image_host(int n, int sign, float* img /* TW_BYTES / 4 floats */, F2 gtw /* gtw(x) -> (cos, sin)(2 pi x / n) */,
+                               int pts = PTS16)
 {
-    const int r2 = n / 16 < 16 ? n / 16 : 16;
-    const int r3 = n / (16 * r2);
+    const int r1 = pts;
+    const int r2 = n / r1 < pts ? n / r1 : pts;
+    const int r3 = n / (r1 * r2);
     const int row = r2 / 2 + 1;                 // float4 per tw2 row
-    const int tw2_f4 = 16 * row;
-    const int tws2 = n / (16 * r2);
+    const int tw2_f4 = r1 * row;
+    const int tws2 = n / (r1 * r2);
     for (int i = 0; i < tw2_f4 * 4; ++i) img[i] = 0.f;
-    for (int k = 0; k < 16; ++k)
+    for (int k = 0; k < r1; ++k)
         for (int r = 0; r < r2; ++r) {
             float c, s;
             gtw((r * k * tws2) % n, c, s);
@@ -229,18 +232,19 @@ inline void twiddle_image_host(int n, int sign, float* img /* TW_BYTES / 4 float
             img[(k * 2 * row + r) * 2 + 1] = sign < 0 ? -s : s;
         }
     if (r3 > 1)
-        for (int i = 0; i < 16 * r2; ++i) {
+        for (int i = 0; i < r1 * r2; ++i) {
             float c, s;
             gtw(i, c, s);
             img[tw2_f4 * 4 + 2 * i + 0] = c;
             img[tw2_f4 * 4 + 2 * i + 1] = sign < 0 ? -s : s;
         }
 }
-inline int twiddle_image_bytes(int n)
+inline int twiddle_image_bytes(int n, int pts = PTS16)
 {
-    const int r2 = n / 16 < 16 ? n / 16 : 16;
-    const int r3 = n / (16 * r2);
-    return 16 * (r2 / 2 + 1) * 16 + (r3 > 1 ? 16 * r2 * 8 : 0);
+    const int r1 = pts;
+    const int r2 = n / r1 < pts ? n / r1 : pts;
+    const int r3 = n / (r1 * r2);
+    return r1 * (r2 / 2 + 1) * 16 + (r3 > 1 ? r1 * r2 * 8 : 0);
 }
 
 __device__ __forceinline__ float2 cmul_s(float2 a, float2 b)
@@ -254,8 +258,8 @@ __host__ __device__ constexpr int pad_step(int m) { return m + m / 16; }
 
 // Hands the R outputs of each of the B butterflies to emit(idx, pidx, value): idx = natural index of the
 // output, pidx = pad_idx(idx) (for emitters that write into a line).
-template <int N, int R, int S, class Emit>
-__device__ __forceinline__ void emit_all(cpk (&v)[PTS], int g, Emit&& emit)
+template <int N, int R, int S, int PTS, class Emit>
+__device__ __forceinline__ void emit_all(cpk* v, int g, Emit&& emit)
 {
     constexpr int T = N / PTS, B = PTS / R, LOGR = ilog2(R);
 #pragma unroll
@@ -270,33 +274,33 @@ __device__ __forceinline__ void emit_all(cpk (&v)[PTS], int g, Emit&& emit)
                 const int rr = bitrev(i, LOGR);
                 emit(base + rr * S, pbase + rr * pad_step(S), v[b + i * B]);
             }
-        } else {  // S == 1: idx = R j + r with R = 16 here, so idx >> 4 == j
-            static_assert(S == 1 && R == 16, "first stage is radix 16");
+        } else {  // S == 1 (first stage, R = PTS, B = 1): idx = R j + r, so pad_idx(idx) = (R + R / 16) j + r + r / 16
+            static_assert(S == 1 && R == PTS && R % 16 == 0, "first stage is radix PTS");
 #pragma unroll
             for (int i = 0; i < R; ++i) {
                 const int rr = bitrev(i, LOGR);
-                emit(base + rr, 17 * j + rr, v[b + i * B]);
+                emit(base + rr, (R + R / 16) * j + rr + rr / 16, v[b + i * B]);
             }
         }
     }
 }
 
-// Stage 1 (radix 16, no twiddles)
-template <int N, int SIGN, class Emit>
-__device__ __forceinline__ void stage1(cpk (&v)[PTS], int g, Emit&& emit)
+// Stage 1 (radix PTS, no twiddles)
+template <int N, int SIGN, int PTS, class Emit>
+__device__ __forceinline__ void stage1(cpk* v, int g, Emit&& emit)
 {
-    dft_all<SIGN, 16, 1>(v);
-    emit_all<N, 16, 1>(v, g, emit);
+    dft_all<SIGN, PTS, 1>(v);
+    emit_all<N, PTS, 1, PTS>(v, g, emit);
 }
-// Stage 2 (radix R2, S = 16): twiddles W_{16 R2}^{r k}, k = j mod 16, one table row per butterfly
-template <int N, int SIGN>
-__device__ __forceinline__ void stage2_compute(cpk (&v)[PTS], int g, const float4* tw2)
+// Stage 2 (radix R2, S = R1): twiddles W_{R1 R2}^{r k}, k = j mod R1, one table row per butterfly
+template <int N, int SIGN, int PTS>
+__device__ __forceinline__ void stage2_compute(cpk* v, int g, const float4* tw2)
 {
-    using P = Plan<N>;
+    using P = Plan<N, PTS>;
     constexpr int R = P::R2, B = PTS / R, T = P::T;
 #pragma unroll
     for (int b = 0; b < B; ++b) {
-        const int k = (g + b * T) & 15;
+        const int k = (g + b * T) & (P::R1 - 1);
         const float4* row = tw2 + k * P::TW2_ROW;
 #pragma unroll
         for (int r2 = 0; r2 < R / 2; ++r2) {
@@ -307,18 +311,18 @@ __device__ __forceinline__ void stage2_compute(cpk (&v)[PTS], int g, const float
     }
     dft_all<SIGN, R, B>(v);
 }
-template <int N, int SIGN, class Emit>
-__device__ __forceinline__ void stage2(cpk (&v)[PTS], int g, const float4* tw2, Emit&& emit)
+template <int N, int SIGN, int PTS, class Emit>
+__device__ __forceinline__ void stage2(cpk* v, int g, const float4* tw2, Emit&& emit)
 {
-    stage2_compute<N, SIGN>(v, g, tw2);
-    emit_all<N, Plan<N>::R2, 16>(v, g, emit);
+    stage2_compute<N, SIGN, PTS>(v, g, tw2);
+    emit_all<N, Plan<N, PTS>::R2, Plan<N, PTS>::R1, PTS>(v, g, emit);
 }
-// Stage 3 (radix R3, S = 16 R2): twiddles W_N^{r k}; w^1 from the table, higher powers by multiplication
-template <int N, int SIGN>
-__device__ __forceinline__ void stage3_compute(cpk (&v)[PTS], int g, const float2* tw3)
+// Stage 3 (radix R3, S = R1 R2): twiddles W_N^{r k}; w^1 from the table, higher powers by multiplication
+template <int N, int SIGN, int PTS>
+__device__ __forceinline__ void stage3_compute(cpk* v, int g, const float2* tw3)
 {
-    using P = Plan<N>;
-    constexpr int R = P::R3, B = PTS / R, T = P::T, S = 16 * P::R2;
+    using P = Plan<N, PTS>;
+    constexpr int R = P::R3, B = PTS / R, T = P::T, S = P::R1 * P::R2;
 #pragma unroll
     for (int b = 0; b < B; ++b) {
         const int k = (g + b * T) & (S - 1);
@@ -331,15 +335,15 @@ __device__ __forceinline__ void stage3_compute(cpk (&v)[PTS], int g, const float
     }
     dft_all<SIGN, R, B>(v);
 }
-template <int N, int SIGN, class Emit>
-__device__ __forceinline__ void stage3(cpk (&v)[PTS], int g, const float2* tw3, Emit&& emit)
+template <int N, int SIGN, int PTS, class Emit>
+__device__ __forceinline__ void stage3(cpk* v, int g, const float2* tw3, Emit&& emit)
 {
-    stage3_compute<N, SIGN>(v, g, tw3);
-    emit_all<N, Plan<N>::R3, 16 * Plan<N>::R2>(v, g, emit);
+    stage3_compute<N, SIGN, PTS>(v, g, tw3);
+    emit_all<N, Plan<N, PTS>::R3, Plan<N, PTS>::R1 * Plan<N, PTS>::R2, PTS>(v, g, emit);
 }
 
-template <int N>
-__device__ __forceinline__ void load_line_regs(cpk (&v)[PTS], const float4* line, int g)
+template <int N, int PTS = PTS16>
+__device__ __forceinline__ void load_line_regs(cpk* v, const float4* line, int g)
 {
     constexpr int T = N / PTS;
     if constexpr (T % 16 == 0) {
@@ -369,6 +373,7 @@ template <int N, int SIGN, class Emit>
 __device__ __forceinline__ void fft_line(float4* line, int g, int line_id, bool active, const float4* tw2,
                                          const float2* tw3, Emit&& emit)
 {
+    constexpr int PTS = PTS16;
     using P = Plan<N>;
     constexpr int T = P::T;
     constexpr int NSYNC = P::R3 == 1 ? 3 : 5;
@@ -377,22 +382,22 @@ __device__ __forceinline__ void fft_line(float4* line, int g, int line_id, bool 
         for (int i = 0; i < NSYNC; ++i) group_sync<T>(line_id);
         return;
     }
-    cpk v[PTS];
+    cpk v[PTS16];
     auto to_smem = [&](int, int pidx, cpk val) { line[pidx] = make_float4(val.re.x, val.re.y, val.im.x, val.im.y); };
     load_line_regs<N>(v, line, g);
     group_sync<T>(line_id);  // everyone has read before anyone overwrites (in-place exchange)
-    stage1<N, SIGN>(v, g, to_smem);
+    stage1<N, SIGN, PTS>(v, g, to_smem);
     group_sync<T>(line_id);
     load_line_regs<N>(v, line, g);
     group_sync<T>(line_id);
     if constexpr (P::R3 == 1) {
-        stage2<N, SIGN>(v, g, tw2, emit);
+        stage2<N, SIGN, PTS>(v, g, tw2, emit);
     } else {
-        stage2<N, SIGN>(v, g, tw2, to_smem);
+        stage2<N, SIGN, PTS>(v, g, tw2, to_smem);
         group_sync<T>(line_id);
         load_line_regs<N>(v, line, g);
         group_sync<T>(line_id);
-        stage3<N, SIGN>(v, g, tw3, emit);
+        stage3<N, SIGN, PTS>(v, g, tw3, emit);
     }
 }
 
@@ -402,18 +407,18 @@ __device__ __forceinline__ void fft_line(float4* line, int g, int line_id, bool 
 // threads that share `line` (the caller chooses the thread <-> line mapping).  There is no "inactive"
 // path on purpose: a group without a real line transforms zeros in its own line buffer, so that every
 // thread of the CTA executes the same barrier instructions (no divergent __syncthreads).
-template <int N>
+template <int N, int PTS = PTS16>
 struct Final {
-    using P = Plan<N>;
+    using P = Plan<N, PTS>;
     static constexpr int R = P::R3 == 1 ? P::R2 : P::R3;
-    static constexpr int S = P::R3 == 1 ? 16 : 16 * P::R2;
+    static constexpr int S = P::R3 == 1 ? P::R1 : P::R1 * P::R2;
     static constexpr int B = PTS / R;
     static constexpr int NSYNC = P::R3 == 1 ? 2 : 4;
 };
-template <int N>
+template <int N, int PTS = PTS16>
 __device__ __forceinline__ int final_idx(int g, int slot)
 {
-    using F = Final<N>;
+    using F = Final<N, PTS>;
     const int b = slot % F::B, i = slot / F::B;
     const int j = g + b * (N / PTS);
     const int k = j & (F::S - 1);
@@ -422,31 +427,30 @@ __device__ __forceinline__ int final_idx(int g, int slot)
 // final_idx<N>(g, slot) == g + final_off<N>(slot): the group index only enters additively, because a thread's
 // butterflies j = g + b T never reach the stage stride S (B T <= S for every plan) -- so every address derived from a
 // result index is "one base + compile-time offset".
-template <int N>
+template <int N, int PTS = PTS16>
 __host__ __device__ constexpr int final_off(int slot)
 {
-    using F = Final<N>;
+    using F = Final<N, PTS>;
     static_assert(F::B * (N / PTS) <= F::S, "j = g + b T must stay below the stage stride");
     return (slot % F::B) * (N / PTS) + bitrev(slot / F::B, ilog2(F::R)) * F::S;
 }
-template <int N, int SIGN, class Sync>
-__device__ __forceinline__ void fft_line_inreg(cpk (&v)[PTS], float4* line, int g, const float4* tw2, const float2* tw3,
-                                               Sync&& sync)
+template <int N, int SIGN, int PTS = PTS16, class Sync>
+__device__ __forceinline__ void fft_line_inreg(cpk* v, float4* line, int g, const float4* tw2, const float2* tw3, Sync&& sync)
 {
-    using P = Plan<N>;
+    using P = Plan<N, PTS>;
     auto to_smem = [&](int, int pidx, cpk val) { line[pidx] = make_float4(val.re.x, val.re.y, val.im.x, val.im.y); };
-    stage1<N, SIGN>(v, g, to_smem);
+    stage1<N, SIGN, PTS>(v, g, to_smem);
     sync();
-    load_line_regs<N>(v, line, g);
+    load_line_regs<N, PTS>(v, line, g);
     sync();  // everyone has read before anyone overwrites (in-place exchange)
     if constexpr (P::R3 == 1) {
-        stage2_compute<N, SIGN>(v, g, tw2);
+        stage2_compute<N, SIGN, PTS>(v, g, tw2);
     } else {
-        stage2<N, SIGN>(v, g, tw2, to_smem);
+        stage2<N, SIGN, PTS>(v, g, tw2, to_smem);
         sync();
-        load_line_regs<N>(v, line, g);
+        load_line_regs<N, PTS>(v, line, g);
         sync();
-        stage3_compute<N, SIGN>(v, g, tw3);
+        stage3_compute<N, SIGN, PTS>(v, g, tw3);
     }
 }
 

@@ -5,6 +5,15 @@
 
 namespace mwk {
 
+// packed points per thread of the FFT engine.  32 (radix 32 x 32: ONE shared-memory exchange per 1024-point transform,
+// one warp per line, no named barriers) is implemented and parity-green, but measured equal-to-slower than 16
+// (radix 16 x 16 x 4, two exchanges) at N = 1024 on B200: 427 vs 423 us per 16-tile frame (profiles/r01_summary.md).
+// Build with -DMW_PTS_1024=32 to select it.
+#ifndef MW_PTS_1024
+#define MW_PTS_1024 16
+#endif
+__host__ __device__ constexpr int fft_pts(int N) { return N == 1024 ? MW_PTS_1024 : 16; }
+
 #ifndef MW_SLABW_1024
 #define MW_SLABW_1024 8
 #endif

@@ -170,7 +170,7 @@ extern "C" int mw_ocean_create(const mw_ocean_params* params, mw_ocean** out)
     if ((rc = ensure(&o->ramp, (size_t)2 * N))) return fail(rc);
     if ((rc = ensure(&o->kd, (size_t)N))) return fail(rc);
     if ((rc = ensure(&o->tw, (size_t)N))) return fail(rc);
-    if ((rc = ensure(&o->twimg, (size_t)mwfft::twiddle_image_bytes(N) / 16))) return fail(rc);
+    if ((rc = ensure(&o->twimg, (size_t)mwfft::twiddle_image_bytes(N, mwk::fft_pts(N)) / 16))) return fail(rc);
     {
         // group size: keep one group's intermediate (24 B per point) around 32 MB
         long long gt = (32ll << 20) / (long long)(o->n2 * 24);
@@ -211,8 +211,8 @@ extern "C" int mw_ocean_create(const mw_ocean_params* params, mw_ocean** out)
         volatile float num = two_pi * d;
         kd[i] = num / p.length;
     }
-    std::vector<float> twimg(mwfft::twiddle_image_bytes(N) / 4);
-    mwfft::twiddle_image_host(N, +1, twimg.data(), [&](int x, float& c, float& s) { c = tw[x].x; s = tw[x].y; });
+    std::vector<float> twimg(mwfft::twiddle_image_bytes(N, mwk::fft_pts(N)) / 4);
+    mwfft::twiddle_image_host(N, +1, twimg.data(), [&](int x, float& c, float& s) { c = tw[x].x; s = tw[x].y; }, mwk::fft_pts(N));
     if (cudaMemcpy(o->tw, tw.data(), N * sizeof(float2), cudaMemcpyHostToDevice) != cudaSuccess ||
         cudaMemcpy(o->twimg, twimg.data(), twimg.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess ||
         cudaMemcpy(o->ramp, ramp.data(), 2 * N * sizeof(float2), cudaMemcpyHostToDevice) != cudaSuccess ||
@@ -393,8 +393,9 @@ extern "C" int mw_ocean_evolve_spectrum(mw_ocean* o, float t, float* htilde)
 template <int N, int RP, int MINB>
 static int launch_rows(mw_ocean* o, const mwk::RowArgs& a, int ntiles, cudaStream_t st)
 {
-    constexpr int threads = RP * 3 * (N / 16);
-    constexpr size_t smem = mwfft::Plan<N>::TW_BYTES + (size_t)RP * 3 * mwfft::line_pitch(N, 8) * sizeof(float4);
+    constexpr int PTS = mwk::fft_pts(N);
+    constexpr int threads = RP * 3 * (N / PTS);
+    constexpr size_t smem = mwfft::Plan<N, PTS>::TW_BYTES + (size_t)RP * 3 * mwfft::line_pitch(N, 8) * sizeof(float4);
     static bool attr_done[64] = {};
     if (!attr_done[o->p.device]) {
         MW_CUDA(cudaFuncSetAttribute(mwk::k_spectrum_rows<N, RP, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -413,8 +414,9 @@ template <int N, int MINB, int OUTS>
 static int launch_cols_outs(mw_ocean* o, mwk::ColArgs a, int ntiles, cudaStream_t st)
 {
     constexpr int W = mwk::slab_w(N);
-    constexpr int threads = (W + 1) * (N / 16);
-    constexpr size_t smem = mwfft::Plan<N>::TW_BYTES + (size_t)(W + 1) * mwfft::line_pitch(N, W) * sizeof(float4) +
+    constexpr int PTS = mwk::fft_pts(N);
+    constexpr int threads = (W + 1) * (N / PTS);
+    constexpr size_t smem = mwfft::Plan<N, PTS>::TW_BYTES + (size_t)(W + 1) * mwfft::line_pitch(N, W) * sizeof(float4) +
                             (size_t)((threads + 31) / 32) * 96 * mwk::nstage_slots(N) * sizeof(float);
     static bool attr_done[64] = {};
     if (!attr_done[o->p.device]) {

@@ -228,9 +228,10 @@ __device__ __forceinline__ float2 htilde_tab(float4 s, float2 e)
 
 // RP row pairs per CTA; 3 packed lines per pair: (A,B) of row rA, (A,B) of row rB, (C of rA, C of rB).
 template <int N, int RP, int MINB>
-__global__ void __launch_bounds__(RP * 3 * (N / 16), MINB) k_spectrum_rows(const RowArgs a)
+__global__ void __launch_bounds__(RP * 3 * (N / fft_pts(N)), MINB) k_spectrum_rows(const RowArgs a)
 {
-    using P = Plan<N>;
+    constexpr int PTS = fft_pts(N);
+    using P = Plan<N, PTS>;
     constexpr int T = P::T;
     constexpr int PAIR_THREADS = 3 * T;
     constexpr int LP = mwfft::line_pitch(N, 8);
@@ -286,7 +287,7 @@ __global__ void __launch_bounds__(RP * 3 * (N / 16), MINB) k_spectrum_rows(const
             e2[it] = __ldg(a.ptab + q2[it]);
         }
         // the twiddle tables are fetched while the spectrum loads are in flight
-        mwfft::load_twiddle_image<N, RP * PAIR_THREADS>(smem4, a.twimg);
+        mwfft::load_twiddle_image<N, RP * PAIR_THREADS, PTS>(smem4, a.twimg);
         const float kxA = __ldg(a.kd + rA), kxB = __ldg(a.kd + rB);
 #pragma unroll
         for (int it = 0; it < NIT; ++it) {
@@ -358,7 +359,7 @@ __global__ void __launch_bounds__(RP * 3 * (N / 16), MINB) k_spectrum_rows(const
             lines[2 * LP + pmm] = make_float4(E3.x, E2.x, E3.y, E2.y);
         }
     } else {
-        mwfft::load_twiddle_image<N, RP * PAIR_THREADS>(smem4, a.twimg);
+        mwfft::load_twiddle_image<N, RP * PAIR_THREADS, PTS>(smem4, a.twimg);
     }
     MW_RSTAMP(1);
     __syncthreads();
@@ -371,12 +372,12 @@ __global__ void __launch_bounds__(RP * 3 * (N / 16), MINB) k_spectrum_rows(const
     {
         // one instance of the transform for all three lines (code size: the kernel has to stay resident in
         // the instruction cache while several CTAs run different phases); results come back in registers
-        mwfft::cpk v[16];
-        mwfft::load_line_regs<N>(v, line, g);
+        mwfft::cpk v[PTS];
+        mwfft::load_line_regs<N, PTS>(v, line, g);
         const int bar_id = rp * 3 + q;
         auto line_sync = [&] { mwfft::group_sync<T>(bar_id); };
         line_sync();  // everyone has read before anyone overwrites (in-place exchange)
-        mwfft::fft_line_inreg<N, +1>(v, line, g, tw2, tw3, line_sync);
+        mwfft::fft_line_inreg<N, +1, PTS>(v, line, g, tw2, tw3, line_sync);
         constexpr int W = slab_w(N);
         if (q < 2) {
             const int row = q ? rB : rA;
@@ -385,13 +386,13 @@ __global__ void __launch_bounds__(RP * 3 * (N / 16), MINB) k_spectrum_rows(const
                 // result index = g + (multiple of T): slab and column-in-slab of g, then compile-time slab steps
                 const unsigned base = ((unsigned)(g / W) * N + row) * W + (g % W);
 #pragma unroll
-                for (int sl = 0; sl < 16; ++sl)
-                    dst[base + (unsigned)(mwfft::final_off<N>(sl) / W) * (N * W)] =
+                for (int sl = 0; sl < PTS; ++sl)
+                    dst[base + (unsigned)(mwfft::final_off<N, PTS>(sl) / W) * (N * W)] =
                         make_float4(v[sl].re.x, v[sl].re.y, v[sl].im.x, v[sl].im.y);
             } else {
 #pragma unroll
-                for (int sl = 0; sl < 16; ++sl)
-                    dst[xab_index(N, row, g + mwfft::final_off<N>(sl))] = make_float4(v[sl].re.x, v[sl].re.y, v[sl].im.x, v[sl].im.y);
+                for (int sl = 0; sl < PTS; ++sl)
+                    dst[xab_index(N, row, g + mwfft::final_off<N, PTS>(sl))] = make_float4(v[sl].re.x, v[sl].re.y, v[sl].im.x, v[sl].im.y);
             }
         } else {
             float2* dst = a.XC + (size_t)xt * N * N;
@@ -399,15 +400,15 @@ __global__ void __launch_bounds__(RP * 3 * (N / 16), MINB) k_spectrum_rows(const
                 const unsigned base = ((unsigned)(g / (2 * W)) * N) * (2 * W) + (g % (2 * W));
                 const unsigned bA = base + (unsigned)rA * (2 * W), bB = base + (unsigned)rB * (2 * W);
 #pragma unroll
-                for (int sl = 0; sl < 16; ++sl) {
-                    const unsigned off = (unsigned)(mwfft::final_off<N>(sl) / (2 * W)) * (N * 2 * W);
+                for (int sl = 0; sl < PTS; ++sl) {
+                    const unsigned off = (unsigned)(mwfft::final_off<N, PTS>(sl) / (2 * W)) * (N * 2 * W);
                     dst[bA + off] = make_float2(v[sl].re.x, v[sl].im.x);
                     dst[bB + off] = make_float2(v[sl].re.y, v[sl].im.y);
                 }
             } else {
 #pragma unroll
-                for (int sl = 0; sl < 16; ++sl) {
-                    const int idx = g + mwfft::final_off<N>(sl);
+                for (int sl = 0; sl < PTS; ++sl) {
+                    const int idx = g + mwfft::final_off<N, PTS>(sl);
                     dst[xc_index(N, rA, idx)] = make_float2(v[sl].re.x, v[sl].im.x);
                     dst[xc_index(N, rB, idx)] = make_float2(v[sl].re.y, v[sl].im.y);
                 }
@@ -474,10 +475,12 @@ __device__ __forceinline__ float rsqrt_ftz(float x)  // argument >= 1 here: no d
 #endif
 __host__ __device__ constexpr int nstage_slots(int N) { return N >= 256 ? MW_NSTAGE : 1; }
 template <int N, int MINB, int OUTS>
-__global__ void __launch_bounds__((slab_w(N) + 1) * (N / 16), MINB) __maxnreg__(N == 1024 ? (MW_SLABW_1024 == 8 ? MW_COLS_MAXREG : 96) : 128) k_cols_extract(const ColArgs a)
+__global__ void __launch_bounds__((slab_w(N) + 1) * (N / fft_pts(N)), MINB)
+__maxnreg__(fft_pts(N) == 32 ? 168 : (N == 1024 ? (MW_SLABW_1024 == 8 ? MW_COLS_MAXREG : 96) : 128)) k_cols_extract(const ColArgs a)
 {
     constexpr int NS = nstage_slots(N);
-    using P = Plan<N>;
+    constexpr int PTS = fft_pts(N);
+    using P = Plan<N, PTS>;
     constexpr int T = P::T;
     constexpr int W = slab_w(N);
     constexpr int LOGW = mwfft::ilog2(W);
@@ -503,7 +506,7 @@ __global__ void __launch_bounds__((slab_w(N) + 1) * (N / 16), MINB) __maxnreg__(
 #define MW_STAMP(i) do { if (a.dbg && tid == 0) a.dbg[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 8 + (i)] = clock64(); } while (0)
     MW_STAMP(0);
 
-    mwfft::cpk v[16];
+    mwfft::cpk v[PTS];
     const bool is_ab = (int)blockIdx.x < a.ab_blocks;
     const bool want_white = OUTS < 0 ? (a.whitecap != nullptr || a.jacobian != nullptr) : (OUTS & 12) != 0;
     const int b0 = is_ab ? blockIdx.x * W : ((int)blockIdx.x - a.ab_blocks) * (2 * W);
@@ -512,7 +515,7 @@ __global__ void __launch_bounds__((slab_w(N) + 1) * (N / 16), MINB) __maxnreg__(
     const bool active = is_ab ? (!is_halo || (want_white && b0 + W < N)) : !is_halo;
     if ((a.dbg_flags & 8) && !is_ab) return;
     if (T >= 32 && !active) {  // whole warps with nothing to transform: help with the tables, then leave
-        mwfft::load_twiddle_image<N, (W + 1) * T>(smem4, a.twimg);
+        mwfft::load_twiddle_image<N, (W + 1) * T, PTS>(smem4, a.twimg);
         return;                // (exited threads are not waited for by barriers)
     }
 
@@ -523,9 +526,9 @@ __global__ void __launch_bounds__((slab_w(N) + 1) * (N / 16), MINB) __maxnreg__(
         const float4* src = a.XAB + (size_t)xt * xab_tile_elems(N) + ((size_t)blockIdx.x * N + g) * W +
                             (is_halo ? (size_t)N * W : (size_t)c);
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
+        for (int k = 0; k < PTS; ++k) {
             float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (active && !(a.dbg_flags & 4)) e = ldg_stream4(src + (size_t)(T * ((k + 8) & 15)) * W);
+            if (active && !(a.dbg_flags & 4)) e = ldg_stream4(src + (size_t)(T * ((k + PTS / 2) & (PTS - 1))) * W);
             v[k].re = make_float2(e.x, e.y);
             v[k].im = make_float2(e.z, e.w);
         }
@@ -533,17 +536,17 @@ __global__ void __launch_bounds__((slab_w(N) + 1) * (N / 16), MINB) __maxnreg__(
         // 16 contiguous bytes = columns b0 + 2c, b0 + 2c + 1 of one row: (re0, im0, re1, im1)
         const float4* src = reinterpret_cast<const float4*>(a.XC + (size_t)xt * plane + ((size_t)(b0 / (2 * W)) * N + g) * (2 * W) + (active ? 2 * c : 0));
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
+        for (int k = 0; k < PTS; ++k) {
             float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (active) e = ldg_stream4(src + (size_t)(T * ((k + 8) & 15)) * W);
+            if (active) e = ldg_stream4(src + (size_t)(T * ((k + PTS / 2) & (PTS - 1))) * W);
             v[k].re = make_float2(e.x, e.z);
             v[k].im = make_float2(e.y, e.w);
         }
     }
     // the twiddle tables are fetched while the slab loads above are in flight
-    mwfft::load_twiddle_image<N, (W + 1) * T>(smem4, a.twimg);
+    mwfft::load_twiddle_image<N, (W + 1) * T, PTS>(smem4, a.twimg);
     MW_STAMP(1);
-    if (!(a.dbg_flags & 2)) mwfft::fft_line_inreg<N, +1>(v, line, g, tw2, tw3, cta_sync);  // one instance for both kinds
+    if (!(a.dbg_flags & 2)) mwfft::fft_line_inreg<N, +1, PTS>(v, line, g, tw2, tw3, cta_sync);  // one instance for both kinds
     MW_STAMP(2);
 
     if (!is_ab) {
@@ -551,8 +554,8 @@ __global__ void __launch_bounds__((slab_w(N) + 1) * (N / 16), MINB) __maxnreg__(
             // height = Re of the finished transform (FFTMesh.cs:219); lane x = column b, lane y = column b + 1
             float* dst = a.height + obase + (size_t)g * N + b0 + 2 * c;
 #pragma unroll
-            for (int s = 0; s < 16; ++s) {
-                const int ar = g + mwfft::final_off<N>(s);
+            for (int s = 0; s < PTS; ++s) {
+                const int ar = g + mwfft::final_off<N, PTS>(s);
                 *reinterpret_cast<float2*>(dst + (size_t)(ar - g) * N) = v[s].re;
             }
         }
@@ -573,17 +576,17 @@ __global__ void __launch_bounds__((slab_w(N) + 1) * (N / 16), MINB) __maxnreg__(
     const bool last_slab = b0 + W >= N;  // CTA-uniform
     float2* D = reinterpret_cast<float2*>(line);
     const int pg = pad_idx(g);
-    auto dpos = [&](int s) { return LINEAR ? pg + mwfft::pad_step(mwfft::final_off<N>(s)) : pad_idx(g + mwfft::final_off<N>(s)); };
+    auto dpos = [&](int s) { return LINEAR ? pg + mwfft::pad_step(mwfft::final_off<N, PTS>(s)) : pad_idx(g + mwfft::final_off<N, PTS>(s)); };
     if (need_d) {
         if (!(is_halo && last_slab)) {
 #pragma unroll
-            for (int s = 0; s < 16; ++s) D[dpos(s)] = make_float2(0.5f * v[s].re.x, 0.5f * v[s].im.x);
-            if (g == T - 1) D[pad_idx(N)] = make_float2(0.5f * v[15].re.x, 0.5f * v[15].im.x);  // slot 15 is row g + N - T
+            for (int s = 0; s < PTS; ++s) D[dpos(s)] = make_float2(0.5f * v[s].re.x, 0.5f * v[s].im.x);
+            if (g == T - 1) D[pad_idx(N)] = make_float2(0.5f * v[PTS - 1].re.x, 0.5f * v[PTS - 1].im.x);  // the last slot is row g + N - T
         }
         if (last_slab && !is_halo && c == W - 1) {
             float2* Dh = reinterpret_cast<float2*>(line + LP);
 #pragma unroll
-            for (int s = 0; s < 16; ++s) Dh[dpos(s)] = make_float2(0.5f * v[s].re.x, 0.5f * v[s].im.x);
+            for (int s = 0; s < PTS; ++s) Dh[dpos(s)] = make_float2(0.5f * v[s].re.x, 0.5f * v[s].im.x);
         }
     }
     __syncthreads();
@@ -611,11 +614,11 @@ __global__ void __launch_bounds__((slab_w(N) + 1) * (N / 16), MINB) __maxnreg__(
                                    : nullptr;
         const bool nrm_lane = lane < 24 && !(a.dbg_flags & 1) && (T >= 32 || tid - lane + W * rr < W * T);  // (small N: rows of halo lanes do not exist)
 #pragma unroll
-        for (int s0 = 0; s0 < 16; s0 += NS) {
+        for (int s0 = 0; s0 < PTS; s0 += NS) {
 #pragma unroll
             for (int j = 0; j < NS; ++j) {
                 const int s = s0 + j;
-                const int off = mwfft::final_off<N>(s);       // output row = g + off
+                const int off = mwfft::final_off<N, PTS>(s);       // output row = g + off
                 const float dx = v[s].re.x, sx = v[s].re.y, dz = v[s].im.x, sz = v[s].im.y;
                 // nor = normalize(up - n) = (sx, 1, sz) / |.|   (FFTMesh.cs:212, 218)
                 const float r2 = fmaf(sx, sx, sz * sz);
@@ -650,7 +653,7 @@ __global__ void __launch_bounds__((slab_w(N) + 1) * (N / 16), MINB) __maxnreg__(
 #pragma unroll
                     for (int j = 0; j < NS; ++j) {
                         const float4 q = *reinterpret_cast<const float4*>(wst + 96 * j + 4 * lane);
-                        p_nrm[(3 * (size_t)mwfft::final_off<N>(s0 + j) * N) / 4] = q;
+                        p_nrm[(3 * (size_t)mwfft::final_off<N, PTS>(s0 + j) * N) / 4] = q;
                     }
                 }
                 __syncwarp();
