@@ -295,7 +295,9 @@ def run_engine(args):
 
     # ---- end to end through the C ABI with HOST buffers (what the C# host calls) ----
     Ke = max(1, min(K, args.e2e_steps))
-    host = mw.Ocean(N, seed=1000 + rank * T, tiles=T, device=local)
+    # MW_HOST_ASYNC: calls enqueue and return; results leave on the handle's copy stream, so the upload of step k + 1
+    # overlaps the download of step k (PCIe is full duplex); everything is complete at host.sync()
+    host = mw.Ocean(N, seed=1000 + rank * T, tiles=T, device=local, host_async=True)
     pin = lambda *shape: torch.empty(*shape, dtype=torch.float32).pin_memory()  # noqa: E731
     h0, h0c = pin(pts_rank, 2), pin(pts_rank, 2)
     host.init_spectrum()
@@ -304,11 +306,13 @@ def run_engine(args):
     for k in range(2):
         host.set_h0(h0, h0c)
         host.generate(0.016 * k, outs)
+    host.sync()
     barrier()
     t0 = time.perf_counter()
     for k in range(Ke):
         host.set_h0(h0, h0c)                 # verttilde / vertConj from host memory, every call
-        host.generate(0.016 * k, outs)       # results land in host arrays; returns after the D2H
+        host.generate(0.016 * k, outs)       # results land in host arrays (complete at sync)
+    host.sync()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     te = torch.tensor([e2e_s], device=dev)
@@ -319,7 +323,7 @@ def run_engine(args):
     host.close()
     e2e = {"value": world * pts_rank * Ke / e2e_s, "unit": UNIT, "h2d_bytes_per_step": pts_rank * 16,
            "d2h_bytes_per_step": pts_rank * 28, "steps": Ke, "ms_per_step": 1e3 * e2e_s / Ke,
-           "api": "mw_ocean_set_h0 + mw_ocean_generate with pinned host buffers", "height_abs_sum_tile0": checksum}
+           "api": "mw_ocean_set_h0 + mw_ocean_generate with pinned host buffers on an MW_HOST_ASYNC handle (upload of step k+1 overlaps download of step k), mw_ocean_sync at the end", "height_abs_sum_tile0": checksum}
 
     # ---- CPU baseline beside it (rank 0, N = 1 only; bounded sample) ----
     cpu = None
@@ -394,7 +398,7 @@ def main():
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--resolution", type=int, default=1024)
     ap.add_argument("--tiles", type=int, default=16)
-    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--cpu-vertices", type=int, default=128, help="vertices in the single-thread CPU baseline sample")
     ap.add_argument("--ref-step-seconds", type=float, default=1.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -50,7 +50,11 @@ enum {
 enum {
     MW_DEVICE_PTRS = 1u << 0, /* buffer arguments are device pointers; calls are stream-async   */
     MW_PROFILE = 1u << 1,     /* record CUDA events around each kernel (mw_ocean_kernel_times) */
-    MW_WRAP_REPEAT = 1u << 2  /* mw_renderer only: border taps wrap around instead of clamping       */
+    MW_WRAP_REPEAT = 1u << 2, /* mw_renderer only: border taps wrap around instead of clamping       */
+    MW_HOST_ASYNC = 1u << 3   /* host-pointer handles only: set_h0 / generate / update enqueue their copies
+                                 and kernels and return at once; the host buffers must be page-locked and stay
+                                 untouched until mw_ocean_sync.  Results leave on a separate copy stream, so the
+                                 upload of the next frame's inputs overlaps the download of this frame's outputs */
 };
 
 /*

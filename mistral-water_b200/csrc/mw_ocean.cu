@@ -37,6 +37,11 @@ struct mw_ocean {
     bool device_ptrs = false;
     bool profile = false;
     bool have_h0 = false;
+    bool host_async = false;              // MW_HOST_ASYNC: host-pointer calls do not wait
+    cudaStream_t copy_stream = nullptr;   // device -> host result copies (host-pointer mode)
+    cudaEvent_t ev_computed = nullptr, ev_copied = nullptr;
+    bool copies_pending = false;
+    float2* s_stage = nullptr;            // [2][tiles][N*N] upload staging of set_h0 (host-pointer mode)
     float timer = 0.f;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
@@ -156,6 +161,7 @@ extern "C" int mw_ocean_create(const mw_ocean_params* params, mw_ocean** out)
     o->n2 = (size_t)o->N * o->N;
     o->device_ptrs = (p.flags & MW_DEVICE_PTRS) != 0;
     o->profile = (p.flags & MW_PROFILE) != 0;
+    o->host_async = (p.flags & MW_HOST_ASYNC) != 0 && !o->device_ptrs;
     const int N = o->N;
     int rc = MW_OK;
     auto fail = [&](int code) { mw_ocean_destroy(o); return code; };
@@ -163,6 +169,13 @@ extern "C" int mw_ocean_create(const mw_ocean_params* params, mw_ocean** out)
         mw_set_error("cudaStreamCreate failed"); return fail(MW_E_CUDA);
     }
     o->stream = o->own_stream;
+    if (!o->device_ptrs) {
+        if (cudaStreamCreateWithFlags(&o->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&o->ev_computed, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&o->ev_copied, cudaEventDisableTiming) != cudaSuccess) {
+            mw_set_error("stream/event creation failed"); return fail(MW_E_CUDA);
+        }
+    }
     if ((rc = ensure(&o->spec, o->n2 * o->tiles))) return fail(rc);
     if ((rc = ensure(&o->spec_r, o->n2 * o->tiles))) return fail(rc);
     if ((rc = ensure(&o->omega, o->n2))) return fail(rc);
@@ -246,8 +259,11 @@ extern "C" void mw_ocean_destroy(mw_ocean* o)
     if (!o) return;
     cudaSetDevice(o->p.device);
     if (o->stream) cudaStreamSynchronize(o->stream);
+    if (o->copy_stream) { cudaStreamSynchronize(o->copy_stream); cudaStreamDestroy(o->copy_stream); }
+    if (o->ev_computed) cudaEventDestroy(o->ev_computed);
+    if (o->ev_copied) cudaEventDestroy(o->ev_copied);
     for (auto& e : o->ev_pool) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
-    void* ptrs[] = {o->spec, o->spec_r, o->qidx, o->ptab, o->twimg, o->omega, o->ramp, o->kd, o->tw, o->XAB, o->s_height, o->s_disp, o->s_normal,
+    void* ptrs[] = {o->s_stage, o->spec, o->spec_r, o->qidx, o->ptab, o->twimg, o->omega, o->ramp, o->kd, o->tw, o->XAB, o->s_height, o->s_disp, o->s_normal,
                     o->s_white, o->s_jac, o->s_vert, o->s_col, o->s_h};
     for (void* q : ptrs) if (q) cudaFree(q);
     for (int i = 0; i < 3; ++i) {
@@ -269,6 +285,8 @@ extern "C" int mw_ocean_sync(mw_ocean* o)
 {
     MW_CHECK_HANDLE(o);
     MW_CUDA(cudaStreamSynchronize(o->stream));
+    if (o->copy_stream) MW_CUDA(cudaStreamSynchronize(o->copy_stream));
+    o->copies_pending = false;
     return MW_OK;
 }
 
@@ -302,10 +320,11 @@ extern "C" int mw_ocean_set_h0(mw_ocean* o, const float* h0, const float* h0conj
     if (!h0 || !h0conj) { mw_set_error("mw_ocean_set_h0: null buffer"); return MW_E_INVALID_ARG; }
     const size_t total = o->n2 * o->tiles;
     const float2 *d0 = (const float2*)h0, *d1 = (const float2*)h0conj;
-    float2* stage = nullptr;
     if (!o->device_ptrs) {
         // stage on the device, then interleave (h0, h0conj) into the packed spectrum
-        MW_CUDA(cudaMallocAsync((void**)&stage, 2 * total * sizeof(float2), o->stream));
+        int rc = ensure(&o->s_stage, 2 * total);
+        if (rc) return rc;
+        float2* stage = o->s_stage;
         MW_CUDA(cudaMemcpyAsync(stage, h0, total * sizeof(float2), cudaMemcpyHostToDevice, o->stream));
         MW_CUDA(cudaMemcpyAsync(stage + total, h0conj, total * sizeof(float2), cudaMemcpyHostToDevice, o->stream));
         d0 = stage; d1 = stage + total;
@@ -314,8 +333,7 @@ extern "C" int mw_ocean_set_h0(mw_ocean* o, const float* h0, const float* h0conj
     MW_LAUNCH_CHECK();
     mwk::k_ramp_spectrum<<<(unsigned)((total + 255) / 256), 256, 0, o->stream>>>(o->spec, o->ramp, o->spec_r, o->N, (int64_t)total);
     MW_LAUNCH_CHECK();
-    if (stage) MW_CUDA(cudaFreeAsync(stage, o->stream));
-    if (!o->device_ptrs) MW_CUDA(cudaStreamSynchronize(o->stream));
+    if (!o->device_ptrs && !o->host_async) MW_CUDA(cudaStreamSynchronize(o->stream));
     o->have_h0 = true;
     return MW_OK;
 }
@@ -535,6 +553,8 @@ extern "C" int mw_ocean_generate(mw_ocean* o, float t, const mw_ocean_out* out)
         else { if ((rc = ensure(&o->s_jac, total))) return rc; d_jac = o->s_jac; }
     }
 
+    // host-pointer mode: the scratch outputs of the previous frame may still be on their way to the host
+    if (!dev && o->copies_pending) MW_CUDA(cudaStreamWaitEvent(o->stream, o->ev_copied, 0));
     // e^{i omega t} for every distinct omega of the grid (one entry per multiple of w0), then the frame
     mwk::k_phase_table<<<(unsigned)((o->q_entries + 255) / 256), 256, 0, o->stream>>>(o->ptab, o->q_entries, o->p.length, t);
     MW_LAUNCH_CHECK();
@@ -559,8 +579,11 @@ extern "C" int mw_ocean_generate(mw_ocean* o, float t, const mw_ocean_out* out)
     }
 
     if (!dev) {
+        // results leave on the copy stream: the main stream is free for the next frame's upload meanwhile
+        MW_CUDA(cudaEventRecord(o->ev_computed, o->stream));
+        MW_CUDA(cudaStreamWaitEvent(o->copy_stream, o->ev_computed, 0));
         auto d2h = [&](void* h, const void* d, size_t bytes) -> cudaError_t {
-            return h ? cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, o->stream) : cudaSuccess;
+            return h ? cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, o->copy_stream) : cudaSuccess;
         };
         MW_CUDA(d2h(out->height, d_height, total * 4));
         MW_CUDA(d2h(out->disp, d_disp, total * 8));
@@ -569,7 +592,12 @@ extern "C" int mw_ocean_generate(mw_ocean* o, float t, const mw_ocean_out* out)
         MW_CUDA(d2h(out->jacobian, d_jac, total * 4));
         MW_CUDA(d2h(out->vertices, d_vert, total * 12));
         MW_CUDA(d2h(out->colors, d_col, total * 16));
-        MW_CUDA(cudaStreamSynchronize(o->stream));
+        MW_CUDA(cudaEventRecord(o->ev_copied, o->copy_stream));
+        o->copies_pending = true;
+        if (!o->host_async) {
+            MW_CUDA(cudaStreamSynchronize(o->copy_stream));
+            o->copies_pending = false;
+        }
     }
     return MW_OK;
 }

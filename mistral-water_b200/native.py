@@ -19,6 +19,7 @@ MW_E_NCCL = -5
 MW_DEVICE_PTRS = 1 << 0
 MW_PROFILE = 1 << 1
 MW_WRAP_REPEAT = 1 << 2
+MW_HOST_ASYNC = 1 << 3
 MW_KERNEL_COUNT = 3
 MW_GERSTNER_MAX_WAVES = 64
 

@@ -38,12 +38,14 @@ class Ocean:
 
     def __init__(self, resolution: int, unit_width: float = 1.0, length: float | None = None,
                  choppiness: float = 1.0, amplitude: float = 0.01, wind=(5.0, 3.0), t_division: float = 1.0,
-                 seed: int = 0, device: int = 0, tiles: int = 1, device_ptrs: bool = False, profile: bool = False):
+                 seed: int = 0, device: int = 0, tiles: int = 1, device_ptrs: bool = False, profile: bool = False,
+                 host_async: bool = False):
         self._lib = native.load()
         self._h = C.c_void_p()
         if length is None:
             length = float(np.float32(resolution) * np.float32(unit_width))
-        flags = (native.MW_DEVICE_PTRS if device_ptrs else 0) | (native.MW_PROFILE if profile else 0)
+        flags = ((native.MW_DEVICE_PTRS if device_ptrs else 0) | (native.MW_PROFILE if profile else 0) |
+                 (native.MW_HOST_ASYNC if host_async else 0))
         self.params = OceanParams(int(resolution), float(unit_width), float(length), float(choppiness),
                                   float(amplitude), float(wind[0]), float(wind[1]), float(t_division),
                                   int(seed) & 0xFFFFFFFFFFFFFFFF, int(device), int(tiles), flags, 0)

@@ -296,6 +296,34 @@ def test_device_pointer_mode_matches_host_mode(mw):
             assert np.array_equal(bufs[k].cpu().numpy().reshape(-1), host[k].reshape(-1)), k
 
 
+def test_host_async_mode_matches_blocking_calls(mw):
+    """MW_HOST_ASYNC: calls return at once, outputs leave on the copy stream; after mw_ocean_sync the pinned host arrays
+    hold exactly what the blocking calls produce, also when frames are queued back to back with a new h0 each."""
+    import torch
+    N, T = 256, 3
+    with mw.Ocean(N, seed=5, tiles=T) as o:
+        o.init_spectrum()
+        h0, hc = o.get_h0()
+        want = [o.generate(0.1 * k) for k in range(3)]
+        o.set_h0(2.0 * h0, hc)
+        want.append(o.generate(0.3))
+    pin = lambda *shape: torch.empty(*shape, dtype=torch.float32).pin_memory()  # noqa: E731
+    ph0, phc = pin(T, N * N, 2), pin(T, N * N, 2)
+    ph0.copy_(torch.from_numpy(h0)); phc.copy_(torch.from_numpy(hc))
+    ph0b = pin(T, N * N, 2); ph0b.copy_(torch.from_numpy(2.0 * h0))
+    outs = [{k: pin(T, N * N, c) for k, c in (("height", 1), ("disp", 2), ("normal", 3), ("whitecap", 1))} for _ in range(4)]
+    with mw.Ocean(N, seed=5, tiles=T, host_async=True) as a:
+        a.set_h0(ph0, phc)
+        for k in range(3):
+            a.generate(0.1 * k, outs[k])
+        a.set_h0(ph0b, phc)
+        a.generate(0.3, outs[3])
+        a.sync()
+        for k in range(4):
+            for name in outs[k]:
+                assert np.array_equal(outs[k][name].numpy(), want[k][name]), (k, name)
+
+
 def test_state_errors(mw):
     with mw.Ocean(64) as o:
         with pytest.raises(mw.native.MwError) as ei:

@@ -84,6 +84,8 @@ def renderer(res, tiles, K=50, label=""):
                       "reference": "44 + 44 + 5 full-texture blits per frame at 16-48 B/texel each (OceanRenderer.cs:216-316)"}), flush=True)
 
 
+if args.only == "renderer16":
+    renderer(128, 16, K=4, label="Ocean Demo scene x 16 oceans per call (profiling run)")
 if args.only in ("", "renderer"):
     renderer(128, 1, label="Ocean Demo scene: resolution 128 -> 1024^2 maps, one ocean per call")
     renderer(128, 16, K=20, label="Ocean Demo scene x 16 oceans per call")

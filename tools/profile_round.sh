@@ -16,6 +16,10 @@ timeout 400 ncu --set full --clock-control none --import-source on -k regex:"k_c
     -o $OUT/${R}_frame_grouped python bench.py --steps 2 --warmup 3 --no-cpu-baseline --e2e-steps 1 > $OUT/${R}_ncu_grouped.log 2>&1
 # (4) Gerstner 32 waves x 1M vertices
 timeout 300 ncu --set full --clock-control none -k regex:k_gerstner -c 1 -o $OUT/${R}_gerstner python tools/bench_extra.py --only gerstner > $OUT/${R}_ncu_gerstner.log 2>&1
+# (4b) OceanRenderer path: Ocean Demo scene (1024^2 maps), 16 oceans per call
+timeout 300 ncu --set full --clock-control none -k regex:"k_r_rows|k_r_cols|k_r_maps" -s 6 -c 3 -o $OUT/${R}_renderer python tools/bench_extra.py --only renderer16 > $OUT/${R}_ncu_renderer.log 2>&1
+# (4c) where the time of the two frame kernels goes: phases switched off one at a time, one launch for all 16 tiles
+MW_GROUP_TILES=16 timeout 200 python tools/phase_timing.py > $OUT/${R}_phases.txt 2>&1
 # (5) the bench line itself + the extra configs (no profiler attached)
 timeout 300 python bench.py > $OUT/${R}_bench.json 2> $OUT/${R}_bench.err
 timeout 300 python tools/bench_extra.py > $OUT/${R}_extra.json 2> $OUT/${R}_extra.err

@@ -15,7 +15,9 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
         "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
         "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
-        "sm__throughput.avg.pct_of_peak_sustained_elapsed"]
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
+        "l1tex__throughput.avg.pct_of_peak_sustained_active", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__inst_executed.avg.per_cycle_elapsed"]
 
 
 def raw(rep):
@@ -42,7 +44,8 @@ md = [f"# profiles/{R}: ncu summaries (B200, sm_100a)\n",
 traffic = {}
 for tag, title in (("frame_grouped", "frame kernels, default scheduling (1 tile of 1024^2 per launch)"),
                    ("frame_batched", "frame kernels, one launch for all 16 tiles (MW_GROUP_TILES=16)"),
-                   ("gerstner", "k_gerstner, 32 waves x 1048576 vertices")):
+                   ("gerstner", "k_gerstner, 32 waves x 1048576 vertices"),
+                   ("renderer", "OceanRenderer path, 16 x (1024^2 maps) per call: k_r_rows, k_r_cols, k_r_maps")):
     rep = os.path.join(G, f"{R}_{tag}.ncu-rep")
     if not os.path.exists(rep):
         continue
@@ -86,6 +89,10 @@ if os.path.exists(lc):
     md.append("")
     with open(os.path.join(P, f"{R}_launches.csv"), "w") as f:
         f.write(open(lc).read())
+ph = os.path.join(G, f"{R}_phases.txt")
+if os.path.exists(ph):
+    md.append("## phases switched off one at a time (`MW_GROUP_TILES=16 python tools/phase_timing.py`, CUDA events per launch, 16 tiles of 1024^2)\n")
+    md.append("```\n" + "".join(l for l in open(ph) if l.startswith("flags=")) + "```\n")
 for fn in (f"{R}_bench.json", f"{R}_extra.json", f"{R}_smi.csv"):
     src = os.path.join(G, fn)
     if os.path.exists(src):
