@@ -67,6 +67,31 @@ __device__ __forceinline__ float2 ldg_stream2(const float2* p)
 }
 
 // ---------------------------------------------------------------------------------------------
+// bulk asynchronous copy global -> shared (the TMA unit's 1-D form) completing on an mbarrier.  One thread issues it; the
+// bytes in flight are tracked by the copy engine, not by the LSU's per-thread request queue.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* mbar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(mbar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* mbar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(mbar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, unsigned bytes, uint64_t* mbar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(mbar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* mbar, unsigned parity)
+{
+    asm volatile("{\n.reg .pred P1;\nMW_WAIT:\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n@P1 bra MW_DONE;\nbra MW_WAIT;\nMW_DONE:\n}"
+                 ::"r"(smem_u32(mbar)), "r"(parity) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
 // Philox4x32-10 (Salmon et al., SC'11), the engine's stand-in for UnityEngine.Random.value.
 // ---------------------------------------------------------------------------------------------
 __host__ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,

@@ -27,5 +27,16 @@ __host__ __device__ constexpr size_t xc_index(int N, int n, int b)
     return ((size_t)(b / (2 * slab_w(N))) * N + n) * (2 * slab_w(N)) + (b % (2 * slab_w(N)));
 }
 __host__ __device__ constexpr size_t xab_tile_elems(int N) { return (size_t)N * N; }
+// FFTMesh-convention C field (float2 units): slabs of 4 W columns; inside a row the columns are ordered so that the 16-byte
+// pair (X[4c], X[4c+1]) of line c sits at float4 position c and (X[4c+2], X[4c+3]) at W + c -- what pass 2 loads with two
+// coalesced instructions -- while pass 1's 32 consecutive columns still fill one contiguous row.
+__host__ __device__ constexpr unsigned xc4_pos(int N, int jj)  // jj = column within the slab
+{
+    return (unsigned)(((jj % 4) / 2) * (2 * slab_w(N)) + (jj / 4) * 2 + (jj % 2));
+}
+__host__ __device__ constexpr size_t xc4_index(int N, int n, int b)
+{
+    return ((size_t)(b / (4 * slab_w(N))) * N + n) * (4 * slab_w(N)) + xc4_pos(N, b % (4 * slab_w(N)));
+}
 
 }  // namespace mwk

@@ -445,7 +445,7 @@ static int launch_cols_outs(mw_ocean* o, mwk::ColArgs a, int ntiles, cudaStream_
     }
     const bool want_ab = a.disp || a.normal || a.whitecap || a.jacobian;
     a.ab_blocks = want_ab ? N / W : 0;
-    const int c_blocks = a.height ? N / (2 * W) : 0;
+    const int c_blocks = a.height ? N / (4 * W) : 0;
     if (a.ab_blocks + c_blocks == 0) return MW_OK;
     dim3 grid(a.ab_blocks + c_blocks, ntiles);
     ProfScope ps(o, 1);
@@ -512,7 +512,11 @@ static int run_frame(mw_ocean* o, const mwk::RowArgs& ra, const mwk::ColArgs& ca
         case 1024: {
             static const int minb = getenv("MW_ROWS_MINB") ? atoi(getenv("MW_ROWS_MINB")) : 3;
             constexpr int CM = MW_SLABW_1024 == 4 ? 2 : 1;
+#if MW_PTS_1024 == 32 && defined(MW_ROWS_RP2)
+            return run_frame_n<1024, 2, 2, CM>(o, ra, ca);   // radix-32 engine: 2 row pairs (6 lines, 192 threads) per CTA
+#else
             return minb == 3 ? run_frame_n<1024, 1, 3, CM>(o, ra, ca) : run_frame_n<1024, 1, 4, CM>(o, ra, ca);
+#endif
         }
         case 2048: return run_frame_n<2048, 1, 1, 1>(o, ra, ca);
     }

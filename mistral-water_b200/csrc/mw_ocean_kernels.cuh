@@ -197,7 +197,7 @@ struct RowArgs {
     const float* kd;       // [N]   2 pi (i - N/2) / L, fp32 as FFTMesh.cs:201
     const float4* twimg;   // shared-memory twiddle tables as a ready-made image (mwfft::twiddle_image_host)
     float4* XAB;           // [tiles][N/8][N][8]
-    float2* XC;            // [tiles][N/16][N][16]
+    float2* XC;            // [tiles][N/32][N][32] (mw_layout.cuh: xc4_index)
     int tile0;             // first tile of this launch (blockIdx.y counts from it); X is indexed by blockIdx.y
     long long* dbg;        // developer phase-timing buffer (NULL in production)
     int dbg_flags;         // developer experiments: 1 = no output stores, 2 = no FFT, 4 = no spectrum loads
@@ -355,8 +355,21 @@ __global__ void __launch_bounds__(RP * 3 * (N / fft_pts(N)), MINB) k_spectrum_ro
             lines[pmm] = F3;
             lines[LP + pm] = F4;
             lines[LP + pmm] = F2;
-            lines[2 * LP + pm] = make_float4(E1.x, E4.x, E1.y, E4.y);
-            lines[2 * LP + pmm] = make_float4(E3.x, E2.x, E3.y, E2.y);
+            // C' is stored Hermitian-symmetrised, Cs(P) = (Eh(P) + conj(Eh(-P))) / 2 (= S / 2 above), Cs(-P) = conj(Cs(P)):
+            // its finished transform is REAL (= height, the real part of the transform of C'), so pass 2 transforms two
+            // columns per complex line (z = column j + i column j') and a C slab covers twice the columns.
+            const float2 Sa = special ? make_float2(0.5f * (E1.x + E3.x), 0.5f * (E1.y - E3.y))    // P1 <-> P3
+                                      : make_float2(0.5f * (E1.x + E2.x), 0.5f * (E1.y - E2.y));   // P1 <-> P2
+            const float2 Sb = special ? make_float2(0.5f * (E4.x + E2.x), 0.5f * (E4.y - E2.y))    // P4 <-> P2
+                                      : make_float2(0.5f * (E3.x + E4.x), 0.5f * (E3.y - E4.y));   // P3 <-> P4
+            // special: Cs(P1) = Sa, Cs(P3) = conj(Sa), Cs(P4) = Sb, Cs(P2) = conj(Sb)
+            // general: Cs(P1) = Sa, Cs(P2) = conj(Sa), Cs(P3) = Sb, Cs(P4) = conj(Sb)
+            const float2 C1 = Sa;
+            const float2 C2 = special ? make_float2(Sb.x, -Sb.y) : make_float2(Sa.x, -Sa.y);
+            const float2 C3 = special ? make_float2(Sa.x, -Sa.y) : Sb;
+            const float2 C4 = special ? Sb : make_float2(Sb.x, -Sb.y);
+            lines[2 * LP + pm] = make_float4(C1.x, C4.x, C1.y, C4.y);
+            lines[2 * LP + pmm] = make_float4(C3.x, C2.x, C3.y, C2.y);
         }
     } else {
         mwfft::load_twiddle_image<N, RP * PAIR_THREADS, PTS>(smem4, a.twimg);
@@ -396,12 +409,13 @@ __global__ void __launch_bounds__(RP * 3 * (N / fft_pts(N)), MINB) k_spectrum_ro
             }
         } else {
             float2* dst = a.XC + (size_t)xt * N * N;
-            if constexpr (T % (2 * W) == 0) {
-                const unsigned base = ((unsigned)(g / (2 * W)) * N) * (2 * W) + (g % (2 * W));
-                const unsigned bA = base + (unsigned)rA * (2 * W), bB = base + (unsigned)rB * (2 * W);
+            if constexpr (T % (4 * W) == 0) {
+                // result column = g + (multiple of T): slab and in-row position of g, then compile-time slab steps
+                const unsigned base = (unsigned)(g / (4 * W)) * N * (4 * W) + xc4_pos(N, g % (4 * W));
+                const unsigned bA = base + (unsigned)rA * (4 * W), bB = base + (unsigned)rB * (4 * W);
 #pragma unroll
                 for (int sl = 0; sl < PTS; ++sl) {
-                    const unsigned off = (unsigned)(mwfft::final_off<N, PTS>(sl) / (2 * W)) * (N * 2 * W);
+                    const unsigned off = (unsigned)(mwfft::final_off<N, PTS>(sl) / (4 * W)) * (N * 4 * W);
                     dst[bA + off] = make_float2(v[sl].re.x, v[sl].im.x);
                     dst[bB + off] = make_float2(v[sl].re.y, v[sl].im.y);
                 }
@@ -409,8 +423,8 @@ __global__ void __launch_bounds__(RP * 3 * (N / fft_pts(N)), MINB) k_spectrum_ro
 #pragma unroll
                 for (int sl = 0; sl < PTS; ++sl) {
                     const int idx = g + mwfft::final_off<N, PTS>(sl);
-                    dst[xc_index(N, rA, idx)] = make_float2(v[sl].re.x, v[sl].im.x);
-                    dst[xc_index(N, rB, idx)] = make_float2(v[sl].re.y, v[sl].im.y);
+                    dst[xc4_index(N, rA, idx)] = make_float2(v[sl].re.x, v[sl].im.x);
+                    dst[xc4_index(N, rB, idx)] = make_float2(v[sl].re.y, v[sl].im.y);
                 }
             }
         }
@@ -423,7 +437,7 @@ __global__ void __launch_bounds__(RP * 3 * (N / fft_pts(N)), MINB) k_spectrum_ro
 // =============================================================================================
 struct ColArgs {
     const float4* XAB;  // [tiles][N/8][N][8]
-    const float2* XC;   // [tiles][N/16][N][16]
+    const float2* XC;   // [tiles][N/32][N][32] Hermitian-symmetrised C' after the row transform (xc4_index)
     const float4* twimg;  // twiddle-table image
     float* height;      // [tiles][N*N]     or NULL
     float2* disp;       // [tiles][N*N]     or NULL   (hds)
@@ -453,7 +467,8 @@ __device__ __forceinline__ float rsqrt_ftz(float x)  // argument >= 1 here: no d
 // 9 packed lines per CTA, two kinds of CTA in one launch:
 //   (A,B) CTA: the (A,B) pairs of W = 8 columns + the halo column b0 + W (so that hds[index + 1] of
 //              FFTMesh.cs:266 is on chip)  -> hds, normal, Jacobian, whitecap
-//   C CTA    : the C field of 16 columns, two columns per packed line (8 lines busy)  -> height
+//   C CTA    : the Hermitian-symmetrised C field of 4 W = 32 columns, FOUR columns per packed line (two real columns per
+//              complex transform; 8 lines busy)  -> height
 //
 // Thread <-> data: thread tid < 8T owns line c = tid & 7 and residue g = tid >> 3 of the line (T = N/16
 // residues), so a warp is 4 consecutive rows x 8 columns.  With that mapping
@@ -509,7 +524,7 @@ __maxnreg__(fft_pts(N) == 32 ? 168 : (N == 1024 ? (MW_SLABW_1024 == 8 ? MW_COLS_
     mwfft::cpk v[PTS];
     const bool is_ab = (int)blockIdx.x < a.ab_blocks;
     const bool want_white = OUTS < 0 ? (a.whitecap != nullptr || a.jacobian != nullptr) : (OUTS & 12) != 0;
-    const int b0 = is_ab ? blockIdx.x * W : ((int)blockIdx.x - a.ab_blocks) * (2 * W);
+    const int b0 = is_ab ? blockIdx.x * W : ((int)blockIdx.x - a.ab_blocks) * (4 * W);
     // a group without a live line (halo group of a C slab, of the last slab, or when no whitecap is wanted)
     // transforms zeros: same instruction stream for every thread, no divergent barrier
     const bool active = is_ab ? (!is_halo || (want_white && b0 + W < N)) : !is_halo;
@@ -521,7 +536,49 @@ __maxnreg__(fft_pts(N) == 32 ? 168 : (N == 1024 ? (MW_SLABW_1024 == 8 ? MW_COLS_
 
     // ---- first-stage inputs straight from global memory: line position p = g + T k holds intermediate row
     //      (p + N/2) mod N = g + T ((k + 8) mod 16)  (the (-1)^a of sigma); slab-major layout => contiguous ----
-    if (is_ab) {
+#ifndef MW_COLS_TMA
+#define MW_COLS_TMA 0
+#endif
+    __shared__ uint64_t slab_bar;
+    if (is_ab && MW_COLS_TMA) {
+        // Build option (-DMW_COLS_TMA=1).  The (A,B) slab is one contiguous block of N * W * 16 bytes (slab-major layout):
+        // ONE thread asks the copy engine for it (cp.async.bulk into the line buffers, which are free until the first stage
+        // writes them), everybody waits on the mbarrier and picks its first-stage inputs out of shared memory.  Measured:
+        // with the intermediate in HBM (one launch for 16 tiles) the load phase shrinks 85 -> 52 us and pass 2 285 -> 267 us
+        // (16 x 576 per-thread loads reach 3.6 TB/s aggregate: the SM's request queue sets the pace, `lg_throttle`); with
+        // the L2-resident intermediate of the default scheduling the extra barrier + shared-memory hop cost more than they
+        // save (frame 426 -> 440 us), hence off by default.
+        float4* raw = lines;  // [N][W] float4, aliases the line buffers
+        if (tid == 0) mbar_init(&slab_bar, 1);
+        __syncthreads();
+        if (tid == 0) {
+            mbar_expect_tx(&slab_bar, (unsigned)(N * W * sizeof(float4)));
+            bulk_g2s(raw, a.XAB + (size_t)xt * xab_tile_elems(N) + (size_t)blockIdx.x * N * W, (unsigned)(N * W * sizeof(float4)), &slab_bar);
+        }
+        if (is_halo) {
+            // the halo column is entry 0 of every row of the NEXT slab: 16 bytes out of each 128-byte row, by plain loads
+            const float4* src = a.XAB + (size_t)xt * xab_tile_elems(N) + ((size_t)blockIdx.x * N + g) * W + (size_t)N * W;
+#pragma unroll
+            for (int k = 0; k < PTS; ++k) {
+                float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (active) e = ldg_stream4(src + (size_t)(T * ((k + PTS / 2) & (PTS - 1))) * W);
+                v[k].re = make_float2(e.x, e.y);
+                v[k].im = make_float2(e.z, e.w);
+            }
+        }
+        mwfft::load_twiddle_image<N, (W + 1) * T, PTS>(smem4, a.twimg);
+        mbar_wait(&slab_bar, 0);
+        if (!is_halo) {
+            const float4* src = raw + g * W + c;
+#pragma unroll
+            for (int k = 0; k < PTS; ++k) {
+                const float4 e = src[(T * ((k + PTS / 2) & (PTS - 1))) * W];
+                v[k].re = make_float2(e.x, e.y);
+                v[k].im = make_float2(e.z, e.w);
+            }
+        }
+        __syncthreads();  // everyone has its inputs before the first stage overwrites the raw slab with the lines
+    } else if (is_ab) {
         // (the halo group, c == W, reads entry 0 of the same row of the next slab, N * W elements further on)
         const float4* src = a.XAB + (size_t)xt * xab_tile_elems(N) + ((size_t)blockIdx.x * N + g) * W +
                             (is_halo ? (size_t)N * W : (size_t)c);
@@ -533,31 +590,38 @@ __maxnreg__(fft_pts(N) == 32 ? 168 : (N == 1024 ? (MW_SLABW_1024 == 8 ? MW_COLS_
             v[k].im = make_float2(e.z, e.w);
         }
     } else {
-        // 16 contiguous bytes = columns b0 + 2c, b0 + 2c + 1 of one row: (re0, im0, re1, im1)
-        const float4* src = reinterpret_cast<const float4*>(a.XC + (size_t)xt * plane + ((size_t)(b0 / (2 * W)) * N + g) * (2 * W) + (active ? 2 * c : 0));
+        // C slab: 4 W columns, line c = columns b0 + 4c .. 4c + 3 as two complex lines z = X[4c] + i X[4c+1] (lane x) and
+        // z = X[4c+2] + i X[4c+3] (lane y): the columns are Hermitian along n (pass 1 stored C' symmetrised), so each
+        // transform is real and Re / Im of the result are the heights of the two columns.  A row of the slab is
+        // [(X0, X1) of the W lines | (X2, X3) of the W lines], 16 bytes each: two fully coalesced loads.
+        const float4* src = reinterpret_cast<const float4*>(a.XC + (size_t)xt * plane + ((size_t)(b0 / (4 * W)) * N + g) * (4 * W)) +
+                            (active ? c : 0);
 #pragma unroll
         for (int k = 0; k < PTS; ++k) {
-            float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (active) e = ldg_stream4(src + (size_t)(T * ((k + PTS / 2) & (PTS - 1))) * W);
-            v[k].re = make_float2(e.x, e.z);
-            v[k].im = make_float2(e.y, e.w);
+            float4 e0 = make_float4(0.f, 0.f, 0.f, 0.f), e1 = e0;
+            if (active) {
+                const float4* p = src + (size_t)(T * ((k + PTS / 2) & (PTS - 1))) * (2 * W);
+                e0 = ldg_stream4(p);
+                e1 = ldg_stream4(p + W);
+            }
+            v[k].re = make_float2(e0.x - e0.w, e1.x - e1.w);
+            v[k].im = make_float2(e0.y + e0.z, e1.y + e1.z);
         }
     }
     // the twiddle tables are fetched while the slab loads above are in flight
-    mwfft::load_twiddle_image<N, (W + 1) * T, PTS>(smem4, a.twimg);
+    if (!(is_ab && MW_COLS_TMA)) mwfft::load_twiddle_image<N, (W + 1) * T, PTS>(smem4, a.twimg);
     MW_STAMP(1);
     if (!(a.dbg_flags & 2)) mwfft::fft_line_inreg<N, +1, PTS>(v, line, g, tw2, tw3, cta_sync);  // one instance for both kinds
     MW_STAMP(2);
 
     if (!is_ab) {
         if (active) {
-            // height = Re of the finished transform (FFTMesh.cs:219); lane x = column b, lane y = column b + 1
-            float* dst = a.height + obase + (size_t)g * N + b0 + 2 * c;
+            // height (FFTMesh.cs:219) of four consecutive columns: (Re, Im) of lane x, (Re, Im) of lane y
+            float* dst = a.height + obase + (size_t)g * N + b0 + 4 * c;
 #pragma unroll
-            for (int s = 0; s < PTS; ++s) {
-                const int ar = g + mwfft::final_off<N, PTS>(s);
-                *reinterpret_cast<float2*>(dst + (size_t)(ar - g) * N) = v[s].re;
-            }
+            for (int s = 0; s < PTS; ++s)
+                *reinterpret_cast<float4*>(dst + (size_t)mwfft::final_off<N, PTS>(s) * N) =
+                    make_float4(v[s].re.x, v[s].im.x, v[s].re.y, v[s].im.y);
         }
         return;
     }
