@@ -660,7 +660,8 @@ __maxnreg__(fft_pts(N) == 32 ? 168 : (N == 1024 ? (MW_SLABW_1024 == 8 ? MW_COLS_
         const bool own = !is_halo && !(a.dbg_flags & 1);  // halo threads run the same code with every memory access predicated off
         if (a.dbg_flags & 16) return;
         const int dn = pad_idx(g + 1) - pg;  // padded distance to the next row (1 or 2)
-        const float2* De = reinterpret_cast<const float2*>(line + LP);  // east neighbour's line
+        // east neighbour's line ((small N) halo threads run along with every access predicated off: keep their reads in bounds)
+        const float2* De = reinterpret_cast<const float2*>(is_halo ? line : line + LP);
         const int lane = tid & 31;
         // per-thread output bases; a slot then adds a compile-time multiple of N
         const size_t o0 = obase + (size_t)g * N + b0 + c;
