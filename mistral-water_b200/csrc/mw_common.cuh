@@ -1,5 +1,6 @@
 // mw_common.cuh -- shared helpers for libmistral_ocean.so (sm_100a only).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -90,6 +91,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* mbar, unsigned parity)
     asm volatile("{\n.reg .pred P1;\nMW_WAIT:\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n@P1 bra MW_DONE;\nbra MW_WAIT;\nMW_DONE:\n}"
                  ::"r"(smem_u32(mbar)), "r"(parity) : "memory");
 }
+
+// 2-D tensor store shared -> global through a CUtensorMap (TMA), bulk-group completion
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, const void* smem_src, int x, int y)
+{
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+                 ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(x), "r"(y), "r"(smem_u32(smem_src)) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ---------------------------------------------------------------------------------------------
 // Philox4x32-10 (Salmon et al., SC'11), the engine's stand-in for UnityEngine.Random.value.

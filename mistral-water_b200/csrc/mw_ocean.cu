@@ -435,7 +435,7 @@ static int launch_cols_outs(mw_ocean* o, mwk::ColArgs a, int ntiles, cudaStream_
     constexpr int PTS = mwk::fft_pts(N);
     constexpr int threads = (W + 1) * (N / PTS);
     constexpr size_t smem = mwfft::Plan<N, PTS>::TW_BYTES + (size_t)(W + 1) * mwfft::line_pitch(N, W) * sizeof(float4) +
-                            (size_t)((threads + 31) / 32) * 96 * mwk::nstage_slots(N) * sizeof(float);
+                            mwk::cols_stage_bytes(N, OUTS, threads);
     static bool attr_done[64] = {};
     if (!attr_done[o->p.device]) {
         MW_CUDA(cudaFuncSetAttribute(mwk::k_cols_extract<N, MINB, OUTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -524,6 +524,30 @@ static int run_frame(mw_ocean* o, const mwk::RowArgs& ra, const mwk::ColArgs& ca
     return MW_E_INVALID_ARG;
 }
 
+// CUtensorMap of one output plane seen as a 2-D float tensor [tiles * N rows][N * comp floats], box = 256 rows x (8 * comp) floats
+static int encode_plane(CUtensorMap* tm, void* base, int N, int tiles, int comp)
+{
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        MW_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres));
+        if (!p || qres != cudaDriverEntryPointSuccess) { mw_set_error("cuTensorMapEncodeTiled not available"); return MW_E_CUDA; }
+        fn = (EncodeFn)p;
+    }
+    const cuuint64_t gdim[2] = {(cuuint64_t)N * comp, (cuuint64_t)tiles * N};
+    const cuuint64_t gstride[1] = {(cuuint64_t)N * comp * sizeof(float)};
+    const cuuint32_t box[2] = {(cuuint32_t)(mwk::slab_w(N) * comp), 256u};
+    const cuuint32_t estride[2] = {1u, 1u};
+    const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { mw_set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return MW_E_CUDA; }
+    return MW_OK;
+}
+
 extern "C" int mw_ocean_generate(mw_ocean* o, float t, const mw_ocean_out* out)
 {
     MW_CHECK_HANDLE(o);
@@ -563,7 +587,13 @@ extern "C" int mw_ocean_generate(mw_ocean* o, float t, const mw_ocean_out* out)
     mwk::k_phase_table<<<(unsigned)((o->q_entries + 255) / 256), 256, 0, o->stream>>>(o->ptab, o->q_entries, o->p.length, t);
     MW_LAUNCH_CHECK();
     mwk::RowArgs ra{o->spec_r, o->qidx, o->ptab, o->kd, o->twimg, o->XAB, o->XC, 0, o->dbg_rows, o->dbg_flags};
-    mwk::ColArgs ca{o->XAB, o->XC, o->twimg, d_height, d_disp, d_normal, d_white, d_jac, o->dbg_cols, o->dbg_flags, 0, 0};
+    mwk::ColArgs ca{};
+    ca.XAB = o->XAB; ca.XC = o->XC; ca.twimg = o->twimg; ca.height = d_height; ca.disp = d_disp; ca.normal = d_normal;
+    ca.whitecap = d_white; ca.jacobian = d_jac; ca.dbg = o->dbg_cols; ca.dbg_flags = o->dbg_flags;
+    if (mwk::cols_tma_store(o->N, (d_disp ? 1 : 0) | (d_normal ? 2 : 0) | (d_white ? 4 : 0) | (d_jac ? 8 : 0))) {
+        if ((rc = encode_plane(&ca.tm_white, d_white, o->N, o->tiles, 1)) || (rc = encode_plane(&ca.tm_disp, d_disp, o->N, o->tiles, 2)) ||
+            (rc = encode_plane(&ca.tm_normal, d_normal, o->N, o->tiles, 3))) return rc;
+    }
     if ((rc = run_frame(o, ra, ca))) return rc;
 
     float* d_vert = nullptr; float4* d_col = nullptr;

@@ -435,6 +435,9 @@ __global__ void __launch_bounds__(RP * 3 * (N / fft_pts(N)), MINB) k_spectrum_ro
 // =============================================================================================
 // pass 2: column FFT + extraction (+ Jacobian whitecap)
 // =============================================================================================
+#ifndef MW_NSTAGE
+#define MW_NSTAGE 4
+#endif
 struct ColArgs {
     const float4* XAB;  // [tiles][N/8][N][8]
     const float2* XC;   // [tiles][N/32][N][32] Hermitian-symmetrised C' after the row transform (xc4_index)
@@ -448,8 +451,22 @@ struct ColArgs {
     int dbg_flags;      // developer experiments (tools/phase_timing.py)
     int tile0;          // first tile of this launch (outputs are indexed by tile0 + blockIdx.y, X by blockIdx.y)
     int ab_blocks;      // blockIdx.x <  ab_blocks : (A,B) slab of 8 columns  (0 if no A/B output is wanted)
-                        // blockIdx.x >= ab_blocks : C slab of 16 columns
+                        // blockIdx.x >= ab_blocks : C slab of 32 columns
+    // TMA descriptors of the whitecap / hds / normal planes as 2-D float tensors [tiles * N rows][N * {1,2,3} floats]
+    // (only read by the kernel variants that store through TMA, see cols_tma_store)
+    alignas(64) CUtensorMap tm_white, tm_disp, tm_normal;
 };
+// Build option (-DMW_COLS_TMA_STORE=1): the (A,B) slab's outputs leave as TMA tensor stores, one 256-row x 8-column box per
+// output plane per chunk, from a shared-memory staging area instead of ~45 per-thread 4..16-byte stores per thread.
+#ifndef MW_COLS_TMA_STORE
+#define MW_COLS_TMA_STORE 0
+#endif
+__host__ __device__ constexpr bool cols_tma_store(int N, int outs) { return MW_COLS_TMA_STORE && N == 1024 && outs == 7 && fft_pts(N) == 16 && slab_w(N) == 8; }
+__host__ __device__ constexpr size_t cols_stage_bytes(int N, int outs, int threads)
+{
+    return cols_tma_store(N, outs) ? (size_t)256 * slab_w(N) * (4 + 8 + 12) + 128
+                                   : (size_t)((threads + 31) / 32) * 96 * (N >= 256 ? MW_NSTAGE : 1) * sizeof(float);
+}
 
 __device__ __forceinline__ float sqrt_approx(float x)
 {
@@ -485,13 +502,10 @@ __device__ __forceinline__ float rsqrt_ftz(float x)  // argument >= 1 here: no d
 #endif
 // OUTS: which (A,B)-slab outputs exist, as a compile-time set (bit 0 hds, 1 normal, 2 whitecap, 3 Jacobian) so that the
 // extraction is straight-line code; OUTS = -1 decides per pointer at run time (any other combination).
-#ifndef MW_NSTAGE
-#define MW_NSTAGE 4
-#endif
 __host__ __device__ constexpr int nstage_slots(int N) { return N >= 256 ? MW_NSTAGE : 1; }
 template <int N, int MINB, int OUTS>
 __global__ void __launch_bounds__((slab_w(N) + 1) * (N / fft_pts(N)), MINB)
-__maxnreg__(fft_pts(N) == 32 ? 168 : (N == 1024 ? (MW_SLABW_1024 == 8 ? MW_COLS_MAXREG : 96) : 128)) k_cols_extract(const ColArgs a)
+__maxnreg__(fft_pts(N) == 32 ? 168 : (N == 1024 ? (MW_SLABW_1024 == 8 ? MW_COLS_MAXREG : 96) : 128)) k_cols_extract(const __grid_constant__ ColArgs a)
 {
     constexpr int NS = nstage_slots(N);
     constexpr int PTS = fft_pts(N);
@@ -656,6 +670,65 @@ __maxnreg__(fft_pts(N) == 32 ? 168 : (N == 1024 ? (MW_SLABW_1024 == 8 ? MW_COLS_
     __syncthreads();
     MW_STAMP(3);
     if (T >= 32 && is_halo) return;  // whole warps: done (for T < 32 they share a warp with owners and stay for the warp syncs)
+    if constexpr (cols_tma_store(N, OUTS)) {
+        // Result slots [ch B, ch B + B) of every thread are the rows g + T b of ONE 256-row chunk of the slab (final_off):
+        // the CTA stages the chunk's whitecap / hds / normal values in the layout of the output rows and one thread hands
+        // the three boxes to the copy engine; the next chunk is computed while the engine reads the staging area.
+        constexpr int FB = mwfft::Final<N, PTS>::B, CHUNK = FB * T;
+        static_assert(CHUNK == 256 && mwfft::Final<N, PTS>::S == 256, "one chunk = 256 consecutive rows");
+        float* stg = nstage + ((128u - (smem_u32(nstage) & 127u)) & 127u) / 4;  // tensor copies want 128-byte aligned shared memory
+        float* st_w = stg;                                                // [256][W]     floats
+        float2* st_d = reinterpret_cast<float2*>(stg + CHUNK * W);        // [256][W]     float2
+        float* st_n = stg + CHUNK * W * 3;                                // [256][3 W]   floats
+        const int dn = pad_idx(g + 1) - pg;
+        const float2* De = reinterpret_cast<const float2*>(line + LP);
+        const int row0 = (a.tile0 + (int)blockIdx.y) * N;
+#pragma unroll
+        for (int ch = 0; ch < PTS / FB; ++ch) {
+            float o_nx[FB], o_ny[FB], o_nz[FB], o_wc[FB];
+#pragma unroll
+            for (int b = 0; b < FB; ++b) {
+                const int s = ch * FB + b;
+                const float dx = v[s].re.x, sx = v[s].re.y, dz = v[s].im.x, sz = v[s].im.y;
+                const float r2 = fmaf(sx, sx, sz * sz);
+                const float inv = rsqrt_ftz(r2 + 1.0f);
+                o_nx[b] = sx * inv; o_ny[b] = inv; o_nz[b] = sz * inv;
+                const int pa = dpos(s);
+                const float2 nbs = D[pa + dn], nbe = De[pa];
+                const float hx = 0.5f * dx, hz = 0.5f * dz;
+                const float ddx_x = hx - nbs.x, ddx_y = hz - nbs.y, ddy_x = hx - nbe.x, ddy_y = hz - nbe.y;
+                const float jac = fmaf(1.0f + ddx_x, 1.0f + ddy_y, -(ddx_y * ddy_x));
+                const float noise = 0.3f * inv * sqrt_approx(r2);
+                float turb = fminf(fmaxf(1.0f - jac + noise, 0.0f), 1.0f);
+                o_wc[b] = turb * turb * fmaf(-2.0f, turb, 3.0f);
+            }
+            if (ch > 0) {  // the engine must have read the previous chunk out of the staging area
+                if (tid == 0) bulk_wait_read();
+                __syncthreads();
+            }
+#pragma unroll
+            for (int b = 0; b < FB; ++b) {
+                const int s = ch * FB + b;
+                const int lr = g + T * b;  // row within the chunk
+                st_w[lr * W + c] = o_wc[b];
+                st_d[lr * W + c] = make_float2(v[s].re.x, v[s].im.x);
+                st_n[lr * 3 * W + 3 * c + 0] = o_nx[b];
+                st_n[lr * 3 * W + 3 * c + 1] = o_ny[b];
+                st_n[lr * 3 * W + 3 * c + 2] = o_nz[b];
+            }
+            fence_proxy_async();
+            __syncthreads();
+            if (tid == 0) {
+                const int y = row0 + mwfft::final_off<N, PTS>(ch * FB);
+                tma_store_2d(&a.tm_white, st_w, b0, y);
+                tma_store_2d(&a.tm_disp, st_d, 2 * b0, y);
+                tma_store_2d(&a.tm_normal, st_n, 3 * b0, y);
+                bulk_commit();
+            }
+        }
+        if (tid == 0) bulk_wait_read();  // the staging area lives as long as this thread does
+        return;
+    }
     {
         const bool own = !is_halo && !(a.dbg_flags & 1);  // halo threads run the same code with every memory access predicated off
         if (a.dbg_flags & 16) return;
