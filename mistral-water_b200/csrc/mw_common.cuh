@@ -67,6 +67,54 @@ __device__ __forceinline__ float2 ldg_stream2(const float2* p)
     return r;
 }
 
+// Streaming variants with an evict-first L2 priority: for data that is touched exactly once (the spectrum on its way in,
+// the outputs on their way out), so that it does not push the pass-1 -> pass-2 intermediate out of the 126 MB L2.
+#ifndef MW_EVICT_FIRST
+#define MW_EVICT_FIRST 1
+#endif
+__device__ __forceinline__ uint64_t evict_first_policy()
+{
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ float4 ldg_once4(const float4* p, uint64_t pol)
+{
+#if MW_EVICT_FIRST
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p), "l"(pol));
+    return r;
+#else
+    (void)pol;
+    return ldg_stream4(p);
+#endif
+}
+__device__ __forceinline__ void st_once(float* p, float v, uint64_t pol)
+{
+#if MW_EVICT_FIRST
+    asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(p), "f"(v), "l"(pol) : "memory");
+#else
+    (void)pol; *p = v;
+#endif
+}
+__device__ __forceinline__ void st_once(float2* p, float2 v, uint64_t pol)
+{
+#if MW_EVICT_FIRST
+    asm volatile("st.global.L2::cache_hint.v2.f32 [%0], {%1,%2}, %3;" ::"l"(p), "f"(v.x), "f"(v.y), "l"(pol) : "memory");
+#else
+    (void)pol; *p = v;
+#endif
+}
+__device__ __forceinline__ void st_once(float4* p, float4 v, uint64_t pol)
+{
+#if MW_EVICT_FIRST
+    asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
+#else
+    (void)pol; *p = v;
+#endif
+}
+
 // ---------------------------------------------------------------------------------------------
 // bulk asynchronous copy global -> shared (the TMA unit's 1-D form) completing on an mbarrier.  One thread issues it; the
 // bytes in flight are tracked by the copy engine, not by the LSU's per-thread request queue.

@@ -262,6 +262,7 @@ __global__ void __launch_bounds__(RP * 3 * (N / fft_pts(N)), MINB) k_spectrum_ro
     //      All loads of a thread's (up to) three tasks are issued before the first use. ----
     if (a.dbg_flags & 512) return;
     if (!(a.dbg_flags & 32)) {
+        const uint64_t pol = evict_first_policy();
         float4 s1[NIT], s2[NIT], s3[NIT], s4[NIT];
         int q1[NIT], q2[NIT];
         float kz[NIT];
@@ -270,10 +271,10 @@ __global__ void __launch_bounds__(RP * 3 * (N / fft_pts(N)), MINB) k_spectrum_ro
             const int m0 = lt + it * PAIR_THREADS;
             const int m = m0 <= N / 2 ? m0 : N / 2;  // surplus threads: harmless repeat of the last task's loads
             const int mm = (N - m) & (N - 1);
-            s1[it] = ldg_stream4(specT + (oA + m));    // P1 = (rA, m)
-            s2[it] = ldg_stream4(specT + (oB + mm));   // P2 = (rB, m')
-            s3[it] = ldg_stream4(specT + (oA + mm));   // P3 = (rA, m')
-            s4[it] = ldg_stream4(specT + (oB + m));    // P4 = (rB, m)
+            s1[it] = ldg_once4(specT + (oA + m), pol);    // P1 = (rA, m)
+            s2[it] = ldg_once4(specT + (oB + mm), pol);   // P2 = (rB, m')
+            s3[it] = ldg_once4(specT + (oA + mm), pol);   // P3 = (rA, m')
+            s4[it] = ldg_once4(specT + (oB + m), pol);    // P4 = (rB, m)
             // omega depends on |k| only: general rows  w(P1) = w(P2), w(P3) = w(P4);
             //                            special rows  w(P1) = w(P3), w(P4) = w(P2)
             q1[it] = __ldg(a.qidx + (oA + m));
@@ -392,6 +393,8 @@ __global__ void __launch_bounds__(RP * 3 * (N / fft_pts(N)), MINB) k_spectrum_ro
         line_sync();  // everyone has read before anyone overwrites (in-place exchange)
         mwfft::fft_line_inreg<N, +1, PTS>(v, line, g, tw2, tw3, line_sync);
         constexpr int W = slab_w(N);
+        // (an evict-last priority on these intermediate stores was measured: no effect once the once-touched traffic is evict-first)
+#define MW_XST(ptr, val) (*(ptr) = (val))
         if (q < 2) {
             const int row = q ? rB : rA;
             float4* dst = a.XAB + (size_t)xt * xab_tile_elems(N);
@@ -400,8 +403,8 @@ __global__ void __launch_bounds__(RP * 3 * (N / fft_pts(N)), MINB) k_spectrum_ro
                 const unsigned base = ((unsigned)(g / W) * N + row) * W + (g % W);
 #pragma unroll
                 for (int sl = 0; sl < PTS; ++sl)
-                    dst[base + (unsigned)(mwfft::final_off<N, PTS>(sl) / W) * (N * W)] =
-                        make_float4(v[sl].re.x, v[sl].re.y, v[sl].im.x, v[sl].im.y);
+                    MW_XST(dst + (base + (unsigned)(mwfft::final_off<N, PTS>(sl) / W) * (N * W)),
+                           make_float4(v[sl].re.x, v[sl].re.y, v[sl].im.x, v[sl].im.y));
             } else {
 #pragma unroll
                 for (int sl = 0; sl < PTS; ++sl)
@@ -416,8 +419,8 @@ __global__ void __launch_bounds__(RP * 3 * (N / fft_pts(N)), MINB) k_spectrum_ro
 #pragma unroll
                 for (int sl = 0; sl < PTS; ++sl) {
                     const unsigned off = (unsigned)(mwfft::final_off<N, PTS>(sl) / (4 * W)) * (N * 4 * W);
-                    dst[bA + off] = make_float2(v[sl].re.x, v[sl].im.x);
-                    dst[bB + off] = make_float2(v[sl].re.y, v[sl].im.y);
+                    MW_XST(dst + (bA + off), make_float2(v[sl].re.x, v[sl].im.x));
+                    MW_XST(dst + (bB + off), make_float2(v[sl].re.y, v[sl].im.y));
                 }
             } else {
 #pragma unroll
@@ -535,6 +538,7 @@ __maxnreg__(fft_pts(N) == 32 ? 168 : (N == 1024 ? (MW_SLABW_1024 == 8 ? MW_COLS_
 #define MW_STAMP(i) do { if (a.dbg && tid == 0) a.dbg[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 8 + (i)] = clock64(); } while (0)
     MW_STAMP(0);
 
+    const uint64_t pol = evict_first_policy();  // outputs are written once and not read again by this engine
     mwfft::cpk v[PTS];
     const bool is_ab = (int)blockIdx.x < a.ab_blocks;
     const bool want_white = OUTS < 0 ? (a.whitecap != nullptr || a.jacobian != nullptr) : (OUTS & 12) != 0;
@@ -634,8 +638,8 @@ __maxnreg__(fft_pts(N) == 32 ? 168 : (N == 1024 ? (MW_SLABW_1024 == 8 ? MW_COLS_
             float* dst = a.height + obase + (size_t)g * N + b0 + 4 * c;
 #pragma unroll
             for (int s = 0; s < PTS; ++s)
-                *reinterpret_cast<float4*>(dst + (size_t)mwfft::final_off<N, PTS>(s) * N) =
-                    make_float4(v[s].re.x, v[s].im.x, v[s].re.y, v[s].im.y);
+                st_once(reinterpret_cast<float4*>(dst + (size_t)mwfft::final_off<N, PTS>(s) * N),
+                        make_float4(v[s].re.x, v[s].im.x, v[s].re.y, v[s].im.y), pol);
         }
         return;
     }
@@ -767,7 +771,7 @@ __maxnreg__(fft_pts(N) == 32 ? 168 : (N == 1024 ? (MW_SLABW_1024 == 8 ? MW_COLS_
                     wst[96 * j + 3 * lane + 1] = inv;
                     wst[96 * j + 3 * lane + 2] = nz;
                 }
-                if (has_disp && own) p_disp[(size_t)off * N] = make_float2(dx, dz);  // hds (FFTMesh.cs:247)
+                if (has_disp && own) st_once(p_disp + (size_t)off * N, make_float2(dx, dz), pol);  // hds (FFTMesh.cs:247)
                 if (need_d) {
                     const int pa = dpos(s);
                     const float2 nbs = D[LINEAR ? pa + dn : pad_idx(g + off + 1)];  // hds[index + resolution] / 2  (:260-263)
@@ -775,13 +779,13 @@ __maxnreg__(fft_pts(N) == 32 ? 168 : (N == 1024 ? (MW_SLABW_1024 == 8 ? MW_COLS_
                     const float hx = 0.5f * dx, hz = 0.5f * dz;
                     const float ddx_x = hx - nbs.x, ddx_y = hz - nbs.y, ddy_x = hx - nbe.x, ddy_y = hz - nbe.y;
                     const float jac = fmaf(1.0f + ddx_x, 1.0f + ddy_y, -(ddx_y * ddy_x));  // :268
-                    if (has_jac && own) p_jac[(size_t)off * N] = jac;
+                    if (has_jac && own) st_once(p_jac + (size_t)off * N, jac, pol);
                     if (has_white && own) {
                         // noise = |(|n.x|, |n.z|) * 0.3| = 0.3 sqrt(sx^2 + sz^2) / |(sx, 1, sz)|   (:269-270)
                         const float noise = 0.3f * inv * sqrt_approx(r2);
                         float turb = fmaxf(1.0f - jac + noise, 0.0f);                           // :270
                         turb = fminf(turb, 1.0f);                                               // SmoothStep clamps
-                        p_white[(size_t)off * N] = turb * turb * fmaf(-2.0f, turb, 3.0f);       // :273
+                        st_once(p_white + (size_t)off * N, turb * turb * fmaf(-2.0f, turb, 3.0f), pol);  // :273
                     }
                 }
             }
@@ -791,7 +795,7 @@ __maxnreg__(fft_pts(N) == 32 ? 168 : (N == 1024 ? (MW_SLABW_1024 == 8 ? MW_COLS_
 #pragma unroll
                     for (int j = 0; j < NS; ++j) {
                         const float4 q = *reinterpret_cast<const float4*>(wst + 96 * j + 4 * lane);
-                        p_nrm[(3 * (size_t)mwfft::final_off<N, PTS>(s0 + j) * N) / 4] = q;
+                        st_once(p_nrm + (3 * (size_t)mwfft::final_off<N, PTS>(s0 + j) * N) / 4, q, pol);
                     }
                 }
                 __syncwarp();

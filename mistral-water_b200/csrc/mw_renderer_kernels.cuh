@@ -143,6 +143,7 @@ __global__ void __launch_bounds__(3 * (N / 16)) k_r_rows(const RRowArgs a)
     float* ph = a.phase + (size_t)tile * N * N;
     const float ky0 = __ldg(a.kw + y0), ky1 = __ldg(a.kw + y1);
     const float two_pi = __fmul_rn(2.0f, MWR_PI_F);
+    const uint64_t pol = evict_first_policy();  // the initial spectrum is read once per frame
     mwfft::load_twiddle_image<N, NT>(smem4, a.twimg);
 
     auto texel = [&](float4 s, float phase_old, float rate, float kx, float ky, unsigned o, float4& F, float2& H) {
@@ -163,7 +164,7 @@ __global__ void __launch_bounds__(3 * (N / 16)) k_r_rows(const RRowArgs a)
 #pragma unroll 2
     for (int x = threadIdx.x; x < N; x += NT) {
         const unsigned o0 = (unsigned)y0 * N + x, o1 = (unsigned)y1 * N + x;
-        const float4 s0 = ldg_stream4(ini + o0), s1 = ldg_stream4(ini + o1);
+        const float4 s0 = ldg_once4(ini + o0, pol), s1 = ldg_once4(ini + o1, pol);
         const float p0 = ph[o0], p1 = ph[o1];
         const float r0 = __ldg(a.rate + o0), r1 = __ldg(a.rate + o1);
         const float kx = __ldg(a.kw + x);
@@ -321,7 +322,8 @@ __global__ void __launch_bounds__(256) k_r_maps(const RMapArgs a)
     const float inv = rsqrtf(sx * sx + sy * sy + sz * sz);
     const float nx = sx * inv, ny = sy * inv, nz = sz * inv;
     const size_t o = base + (size_t)y * R + x;
-    if (a.normal) a.normal[o] = make_float4(nx, ny, nz, 1.0f);
+    const uint64_t pol = evict_first_policy();  // the maps leave the engine here
+    if (a.normal) st_once(a.normal + o, make_float4(nx, ny, nz, 1.0f), pol);
     if (a.white || a.white_rgba || a.jacobian) {
         // WhiteCap.shader:35-36: +-step texel central differences of disp.rb, / 8
         const int st = a.step;
@@ -334,9 +336,9 @@ __global__ void __launch_bounds__(256) k_r_maps(const RMapArgs a)
         const float turb = fmaxf(0.0f, 1.0f - jac + sqrtf(ax * ax + az * az));             // :39
         const float s = fminf(turb, 1.0f);
         const float xx = s * s * (3.0f - 2.0f * s);                                         // :42 smoothstep(0, 1, turb)
-        if (a.white) a.white[o] = xx;
-        if (a.white_rgba) a.white_rgba[o] = make_float4(xx, xx, xx, 1.0f);
-        if (a.jacobian) a.jacobian[o] = jac;
+        if (a.white) st_once(a.white + o, xx, pol);
+        if (a.white_rgba) st_once(a.white_rgba + o, make_float4(xx, xx, xx, 1.0f), pol);
+        if (a.jacobian) st_once(a.jacobian + o, jac, pol);
     }
 }
 
