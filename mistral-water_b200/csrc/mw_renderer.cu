@@ -20,9 +20,13 @@ struct mw_renderer {
     float* rate = nullptr;      // [R][R]
     float* kw = nullptr;        // [R]
     float4* twimg = nullptr;
-    float4* XAB = nullptr;      // intermediate of one tile group
+    float4* XAB = nullptr;      // intermediate: two slots of one tile group each
     float2* XC = nullptr;
-    int group_tiles = 1;
+    int group_tiles = 1, x_tiles = 1;
+    // tile-group pipelining as in the FFTMesh path: groups alternate between two streams and two slots of the
+    // intermediate, so that pass 1 of one group overlaps pass 2 of the previous one and the intermediate stays in L2
+    cudaStream_t aux_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     // scratch images (host-pointer mode, or inputs of pass 3 the caller did not ask for)
     float4* s_disp = nullptr; float4* s_height = nullptr; float4* s_normal = nullptr; float* s_white = nullptr;
     float4* s_white4 = nullptr; float* s_jac = nullptr;
@@ -50,6 +54,9 @@ extern "C" void mw_renderer_destroy(mw_renderer* r)
     void* ptrs[] = {r->initial, r->phase, r->rate, r->kw, r->twimg, r->XAB, r->s_disp, r->s_height, r->s_normal,
                     r->s_white, r->s_white4, r->s_jac};
     for (void* q : ptrs) if (q) cudaFree(q);
+    if (r->aux_stream) { cudaStreamSynchronize(r->aux_stream); cudaStreamDestroy(r->aux_stream); }
+    if (r->ev_fork) cudaEventDestroy(r->ev_fork);
+    if (r->ev_join) cudaEventDestroy(r->ev_join);
     if (r->stream) cudaStreamDestroy(r->stream);
     delete r;
 }
@@ -117,9 +124,15 @@ extern "C" int mw_renderer_create(const mw_renderer_params* params, mw_renderer*
         if (gt < 1) gt = 1;
         if (gt > r->tiles) gt = r->tiles;
         r->group_tiles = (int)gt;
+        r->x_tiles = r->tiles <= r->group_tiles ? r->tiles : 2 * r->group_tiles;
         char* x = nullptr;
-        const size_t xab_bytes = r->n2 * sizeof(float4) * r->group_tiles;
-        if ((rc = r_ensure(&x, xab_bytes + r->n2 * r->group_tiles * 8))) return fail(rc);
+        const size_t xab_bytes = r->n2 * sizeof(float4) * r->x_tiles;
+        if ((rc = r_ensure(&x, xab_bytes + r->n2 * r->x_tiles * 8))) return fail(rc);
+        if (cudaStreamCreateWithFlags(&r->aux_stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&r->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&r->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+            mw_set_error("stream/event creation failed"); return fail(MW_E_CUDA);
+        }
         r->XAB = reinterpret_cast<float4*>(x);
         r->XC = reinterpret_cast<float2*>(x + xab_bytes);
     }
@@ -226,14 +239,29 @@ static int run_renderer_frame(mw_renderer* r, float dt, float4* d_disp, float4* 
         attr_done[r->p.device] = true;
     }
     const int G = r->group_tiles;
-    for (int t0 = 0; t0 < r->tiles; t0 += G) {
+    const int ngroups = (r->tiles + G - 1) / G;
+    const bool dual = ngroups > 1;
+    if (dual) {
+        MW_CUDA(cudaEventRecord(r->ev_fork, r->stream));
+        MW_CUDA(cudaStreamWaitEvent(r->aux_stream, r->ev_fork, 0));
+    }
+    for (int gi = 0; gi < ngroups; ++gi) {
+        const int t0 = gi * G;
         const int nt = r->tiles - t0 < G ? r->tiles - t0 : G;
-        mwr::RRowArgs ra{r->initial, r->phase, r->rate, r->kw, r->twimg, r->XAB, r->XC, dt, r->p.choppiness, t0};
-        mwr::k_r_rows<N><<<dim3(N / 2, nt), 3 * T, smem_r, r->stream>>>(ra);
+        const int slot = dual ? (gi & 1) : 0;
+        cudaStream_t st = (dual && slot) ? r->aux_stream : r->stream;
+        float4* xab = r->XAB + (size_t)slot * G * r->n2;
+        float2* xc = r->XC + (size_t)slot * G * r->n2;
+        mwr::RRowArgs ra{r->initial, r->phase, r->rate, r->kw, r->twimg, xab, xc, dt, r->p.choppiness, t0};
+        mwr::k_r_rows<N><<<dim3(N / 2, nt), 3 * T, smem_r, st>>>(ra);
         MW_LAUNCH_CHECK();
-        mwr::RColArgs ca{r->XAB, r->XC, r->twimg, d_disp, d_height, t0, N / W};
-        mwr::k_r_cols<N><<<dim3(N / W + N / (2 * W), nt), W * T, smem_c, r->stream>>>(ca);
+        mwr::RColArgs ca{xab, xc, r->twimg, d_disp, d_height, t0, N / W};
+        mwr::k_r_cols<N><<<dim3(N / W + N / (2 * W), nt), W * T, smem_c, st>>>(ca);
         MW_LAUNCH_CHECK();
+    }
+    if (dual) {
+        MW_CUDA(cudaEventRecord(r->ev_join, r->aux_stream));
+        MW_CUDA(cudaStreamWaitEvent(r->stream, r->ev_join, 0));
     }
     return MW_OK;
 }
