@@ -52,6 +52,30 @@ __device__ __forceinline__ float2 cmul(float2 a, float2 b)
 }
 __device__ __forceinline__ float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
 
+// Programmatic dependent launch (sm_90+): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may
+// become resident while its predecessor in the stream is still running.  pdl_wait() blocks until the predecessor grid has
+// completed and its writes are visible (a no-op for a normal launch); pdl_trigger() tells the scheduler that this CTA no
+// longer minds the successor's CTAs being placed (they take free slots only and park at their own pdl_wait()).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// Host side: launch `kern(arg)`; with pdl the launch carries the programmatic-serialisation attribute.
+template <class Kern, class Arg>
+static inline cudaError_t mw_launch(Kern kern, dim3 grid, unsigned threads, size_t smem, cudaStream_t st, bool pdl, const Arg& arg)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(threads, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, arg);
+}
+
 // streaming (read-once / write-once) global accesses: keep them out of L1
 __device__ __forceinline__ float4 ldg_stream4(const float4* p)
 {

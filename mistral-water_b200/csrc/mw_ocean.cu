@@ -66,6 +66,8 @@ struct mw_ocean {
     // streams and two slots of the intermediate buffer, so that (a) the intermediate of a group stays in the
     // 126 MB L2 between pass 1 and pass 2 and (b) pass 1 of one group overlaps pass 2 of the previous one
     int group_tiles = 1, x_tiles = 1, slots = 2;
+    // programmatic dependent launch of the frame kernels (MW_PDL=0 off, 1 = successors released at CTA start, 2 = late)
+    int pdl = 1;
     cudaStream_t aux_stream[3] = {nullptr, nullptr, nullptr};   // streams 1..slots-1 (stream 0 is the caller's)
     cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
     long long* dbg_rows = nullptr; long long* dbg_cols = nullptr;  // developer phase timing (mw_debug_phase_buffers)
@@ -191,6 +193,7 @@ extern "C" int mw_ocean_create(const mw_ocean_params* params, mw_ocean** out)
         if (gt < 1) gt = 1;
         if (gt > o->tiles) gt = o->tiles;
         o->group_tiles = (int)gt;
+        if (const char* e = getenv("MW_PDL")) o->pdl = atoi(e);
         if (const char* e = getenv("MW_SLOTS")) o->slots = atoi(e);
         if (o->slots < 2) o->slots = 2;
         if (o->slots > 4) o->slots = 4;
@@ -423,7 +426,7 @@ static int launch_rows(mw_ocean* o, const mwk::RowArgs& a, int ntiles, cudaStrea
     }
     dim3 grid(N / 2 / RP, ntiles);
     ProfScope ps(o, 0);
-    mwk::k_spectrum_rows<N, RP, MINB><<<grid, threads, smem, st>>>(a);
+    MW_CUDA(mw_launch(mwk::k_spectrum_rows<N, RP, MINB>, grid, threads, smem, st, o->pdl != 0, a));
     MW_LAUNCH_CHECK();
     return MW_OK;
 }
@@ -449,7 +452,7 @@ static int launch_cols_outs(mw_ocean* o, mwk::ColArgs a, int ntiles, cudaStream_
     if (a.ab_blocks + c_blocks == 0) return MW_OK;
     dim3 grid(a.ab_blocks + c_blocks, ntiles);
     ProfScope ps(o, 1);
-    mwk::k_cols_extract<N, MINB, OUTS><<<grid, threads, smem, st>>>(a);
+    MW_CUDA(mw_launch(mwk::k_cols_extract<N, MINB, OUTS>, grid, threads, smem, st, o->pdl != 0, a));
     MW_LAUNCH_CHECK();
     return MW_OK;
 }
@@ -586,10 +589,10 @@ extern "C" int mw_ocean_generate(mw_ocean* o, float t, const mw_ocean_out* out)
     // e^{i omega t} for every distinct omega of the grid (one entry per multiple of w0), then the frame
     mwk::k_phase_table<<<(unsigned)((o->q_entries + 255) / 256), 256, 0, o->stream>>>(o->ptab, o->q_entries, o->p.length, t);
     MW_LAUNCH_CHECK();
-    mwk::RowArgs ra{o->spec_r, o->qidx, o->ptab, o->kd, o->twimg, o->XAB, o->XC, 0, o->dbg_rows, o->dbg_flags};
+    mwk::RowArgs ra{o->spec_r, o->qidx, o->ptab, o->kd, o->twimg, o->XAB, o->XC, 0, o->dbg_rows, o->dbg_flags, o->pdl};
     mwk::ColArgs ca{};
     ca.XAB = o->XAB; ca.XC = o->XC; ca.twimg = o->twimg; ca.height = d_height; ca.disp = d_disp; ca.normal = d_normal;
-    ca.whitecap = d_white; ca.jacobian = d_jac; ca.dbg = o->dbg_cols; ca.dbg_flags = o->dbg_flags;
+    ca.whitecap = d_white; ca.jacobian = d_jac; ca.dbg = o->dbg_cols; ca.dbg_flags = o->dbg_flags; ca.pdl = o->pdl;
     if (mwk::cols_tma_store(o->N, (d_disp ? 1 : 0) | (d_normal ? 2 : 0) | (d_white ? 4 : 0) | (d_jac ? 8 : 0))) {
         if ((rc = encode_plane(&ca.tm_white, d_white, o->N, o->tiles, 1)) || (rc = encode_plane(&ca.tm_disp, d_disp, o->N, o->tiles, 2)) ||
             (rc = encode_plane(&ca.tm_normal, d_normal, o->N, o->tiles, 3))) return rc;

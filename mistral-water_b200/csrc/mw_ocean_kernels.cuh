@@ -52,6 +52,7 @@ __global__ void k_dispersion(float* __restrict__ omega, int* __restrict__ qidx, 
 // Per frame: ptab[q] = (cos, sin)(fl(fl(q * w0) * t)), FFTMesh.cs:183-185 for every distinct omega of the grid.
 __global__ void k_phase_table(float2* __restrict__ ptab, int entries, float length, float t)
 {
+    pdl_trigger();  // pass 1 of the first tile group may become resident and fetch its spectrum meanwhile
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= entries) return;
     const float omegat = __fmul_rn(__fmul_rn((float)q, dispersion_w0(length)), t);
@@ -201,6 +202,7 @@ struct RowArgs {
     int tile0;             // first tile of this launch (blockIdx.y counts from it); X is indexed by blockIdx.y
     long long* dbg;        // developer phase-timing buffer (NULL in production)
     int dbg_flags;         // developer experiments: 1 = no output stores, 2 = no FFT, 4 = no spectrum loads
+    int pdl;               // programmatic dependent launch: 1 = release the successor at CTA start, 2 = before the result stores
 };
 
 // Signs.  The direct sum equals sigma[a,b] * T[a,b] with sigma = -(-1)^(a+b), and Dz carries an
@@ -250,6 +252,7 @@ __global__ void __launch_bounds__(RP * 3 * (N / fft_pts(N)), MINB) k_spectrum_ro
 
 #define MW_RSTAMP(i) do { if (a.dbg && threadIdx.x == 0) a.dbg[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 8 + (i)] = clock64(); } while (0)
     MW_RSTAMP(0);
+    if (a.pdl == 1) pdl_trigger();
 
     const bool special = pair == 0;         // rows 0 and N/2 mirror onto themselves
     const int rA = special ? 0 : pair;
@@ -281,6 +284,9 @@ __global__ void __launch_bounds__(RP * 3 * (N / fft_pts(N)), MINB) k_spectrum_ro
             q2[it] = __ldg(a.qidx + (special ? oB + m : oA + mm));
             kz[it] = __ldg(a.kd + m);
         }
+        // Everything fetched so far is constant across frames.  The phase table is this frame's (k_phase_table), and the
+        // intermediate written below may still be being read by the previous pass 2 of this stream: wait for the predecessor.
+        pdl_wait();
         float2 e1[NIT], e2[NIT];
 #pragma unroll
         for (int it = 0; it < NIT; ++it) {
@@ -374,6 +380,7 @@ __global__ void __launch_bounds__(RP * 3 * (N / fft_pts(N)), MINB) k_spectrum_ro
         }
     } else {
         mwfft::load_twiddle_image<N, RP * PAIR_THREADS, PTS>(smem4, a.twimg);
+        pdl_wait();
     }
     MW_RSTAMP(1);
     __syncthreads();
@@ -392,6 +399,7 @@ __global__ void __launch_bounds__(RP * 3 * (N / fft_pts(N)), MINB) k_spectrum_ro
         auto line_sync = [&] { mwfft::group_sync<T>(bar_id); };
         line_sync();  // everyone has read before anyone overwrites (in-place exchange)
         mwfft::fft_line_inreg<N, +1, PTS>(v, line, g, tw2, tw3, line_sync);
+        if (a.pdl == 2) pdl_trigger();
         constexpr int W = slab_w(N);
         // (an evict-last priority on these intermediate stores was measured: no effect once the once-touched traffic is evict-first)
 #define MW_XST(ptr, val) (*(ptr) = (val))
@@ -453,6 +461,7 @@ struct ColArgs {
     long long* dbg;     // developer phase-timing buffer (NULL in production): 8 clock64 stamps per CTA
     int dbg_flags;      // developer experiments (tools/phase_timing.py)
     int tile0;          // first tile of this launch (outputs are indexed by tile0 + blockIdx.y, X by blockIdx.y)
+    int pdl;            // programmatic dependent launch: 1 = release the successor at CTA start, 2 = before the extraction
     int ab_blocks;      // blockIdx.x <  ab_blocks : (A,B) slab of 8 columns  (0 if no A/B output is wanted)
                         // blockIdx.x >= ab_blocks : C slab of 32 columns
     // TMA descriptors of the whitecap / hds / normal planes as 2-D float tensors [tiles * N rows][N * {1,2,3} floats]
@@ -546,12 +555,14 @@ __maxnreg__(fft_pts(N) == 32 ? 168 : (N == 1024 ? (MW_SLABW_1024 == 8 ? MW_COLS_
     // a group without a live line (halo group of a C slab, of the last slab, or when no whitecap is wanted)
     // transforms zeros: same instruction stream for every thread, no divergent barrier
     const bool active = is_ab ? (!is_halo || (want_white && b0 + W < N)) : !is_halo;
+    if (a.pdl == 1) pdl_trigger();
     if ((a.dbg_flags & 8) && !is_ab) return;
     if (T >= 32 && !active) {  // whole warps with nothing to transform: help with the tables, then leave
         mwfft::load_twiddle_image<N, (W + 1) * T, PTS>(smem4, a.twimg);
         return;                // (exited threads are not waited for by barriers)
     }
 
+    pdl_wait();  // the intermediate is pass 1's (the predecessor in this stream)
     // ---- first-stage inputs straight from global memory: line position p = g + T k holds intermediate row
     //      (p + N/2) mod N = g + T ((k + 8) mod 16)  (the (-1)^a of sigma); slab-major layout => contiguous ----
 #ifndef MW_COLS_TMA
@@ -631,6 +642,7 @@ __maxnreg__(fft_pts(N) == 32 ? 168 : (N == 1024 ? (MW_SLABW_1024 == 8 ? MW_COLS_
     MW_STAMP(1);
     if (!(a.dbg_flags & 2)) mwfft::fft_line_inreg<N, +1, PTS>(v, line, g, tw2, tw3, cta_sync);  // one instance for both kinds
     MW_STAMP(2);
+    if (a.pdl == 2) pdl_trigger();
 
     if (!is_ab) {
         if (active) {
