@@ -138,15 +138,18 @@ def run_reference(args):
     emit(line)
 
 
-def workload_config(args, world):
+def workload_config(args, world, gather_impl="nccl"):
     N, T = args.resolution, args.tiles
+    coll = ("one in-place all-gather of the final float buffers per step, over NVLink peer memory: every rank's copy engines "
+            "push its slot into the peers' buffers (CUDA IPC), two 4-byte NCCL all-reduces fence the step"
+            if gather_impl == "p2p" else "one in-place all-gather of the final float buffers (NCCL) per step")
     return {
         "workload": f"{T} x ({N}x{N} Tessendorf grid, height+hds+normal+Jacobian whitecap) per GPU per step "
                     f"= BASELINE configs[2] batched",
         "resolution": N, "tiles_per_gpu": T, "points_per_step_per_gpu": T * N * N,
         "outputs": "height,hds,normal,whitecap (28 B/pt)", "algorithmic_bytes_per_point": ALG_BYTES_PIPELINE,
         "l2": f"inputs {T * N * N * 16 / 1e6:.0f} MB + outputs {T * N * N * 28 / 1e6:.0f} MB per step > 126 MB L2; no flush",
-        "collective": "none" if world == 1 else "one in-place all-gather of the final float buffers (NCCL) per step",
+        "collective": "none" if world == 1 else coll,
         "parallelism": f"tiles{world}",
     }
 
@@ -342,7 +345,7 @@ def run_engine(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic (device Philox4x32-10 + Phillips spectrum, seed 1000+tile)",
-            "config": workload_config(args, world), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+            "config": workload_config(args, world, st.gather_impl), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roof, "cpu_baseline": cpu,
             "achieved_hbm_gbs_pipeline": round(ALG_BYTES_PIPELINE * pts_rank * K / (compute_ms * 1e-3) / 1e9, 1),
         }
@@ -352,7 +355,7 @@ def run_engine(args):
                 "compute_only_value": world * pts_rank * K / (compute_ms * 1e-3), "compute_ms_per_step": compute_ms / K,
                 "allgather_ms_per_step": gather_ms / K, "allgather_bytes_per_rank": slot,
                 "allgather_busbw_gbs": round(slot * (world - 1) / (gather_ms / K * 1e-3) / 1e9, 1) if gather_ms else None,
-                "nvlink_peer_copy_peak_gbs": 770.0,
+                "nvlink_peer_copy_peak_gbs": 770.0, "gather_impl": st.gather_impl, "p2p_error": st.p2p_error,
             }
         emit(line)
     st.close()

@@ -23,6 +23,7 @@ struct mw_renderer {
     float4* XAB = nullptr;      // intermediate: two slots of one tile group each
     float2* XC = nullptr;
     int group_tiles = 1, x_tiles = 1;
+    bool pdl = true;   // programmatic dependent launch of the frame kernels (MW_PDL=0 switches it off)
     // tile-group pipelining as in the FFTMesh path: groups alternate between two streams and two slots of the
     // intermediate, so that pass 1 of one group overlaps pass 2 of the previous one and the intermediate stays in L2
     cudaStream_t aux_stream = nullptr;
@@ -124,6 +125,7 @@ extern "C" int mw_renderer_create(const mw_renderer_params* params, mw_renderer*
         if (gt < 1) gt = 1;
         if (gt > r->tiles) gt = r->tiles;
         r->group_tiles = (int)gt;
+        if (const char* e = getenv("MW_PDL")) r->pdl = atoi(e) != 0;
         r->x_tiles = r->tiles <= r->group_tiles ? r->tiles : 2 * r->group_tiles;
         char* x = nullptr;
         const size_t xab_bytes = r->n2 * sizeof(float4) * r->x_tiles;
@@ -253,10 +255,10 @@ static int run_renderer_frame(mw_renderer* r, float dt, float4* d_disp, float4* 
         float4* xab = r->XAB + (size_t)slot * G * r->n2;
         float2* xc = r->XC + (size_t)slot * G * r->n2;
         mwr::RRowArgs ra{r->initial, r->phase, r->rate, r->kw, r->twimg, xab, xc, dt, r->p.choppiness, t0};
-        mwr::k_r_rows<N><<<dim3(N / 2, nt), 3 * T, smem_r, st>>>(ra);
+        MW_CUDA(mw_launch(mwr::k_r_rows<N>, dim3(N / 2, nt), 3 * T, smem_r, st, r->pdl, ra));
         MW_LAUNCH_CHECK();
         mwr::RColArgs ca{xab, xc, r->twimg, d_disp, d_height, t0, N / W};
-        mwr::k_r_cols<N><<<dim3(N / W + N / (2 * W), nt), W * T, smem_c, st>>>(ca);
+        MW_CUDA(mw_launch(mwr::k_r_cols<N>, dim3(N / W + N / (2 * W), nt), W * T, smem_c, st, r->pdl, ca));
         MW_LAUNCH_CHECK();
     }
     if (dual) {
@@ -306,7 +308,7 @@ extern "C" int mw_renderer_generate_texture(mw_renderer* r, float delta_time, co
     if (d_normal || want_white) {
         mwr::RMapArgs ma{d_disp, d_height, d_normal, d_white, d_white4, d_jac, r->R, r->tiles, r->R / r->p.resolution,
                          (r->p.flags & MW_WRAP_REPEAT) ? 1 : 0, r->p.length / (float)r->R};
-        mwr::k_r_maps<<<dim3((r->R + 31) / 32, (r->R + 7) / 8, r->tiles), 256, 0, r->stream>>>(ma);
+        MW_CUDA(mw_launch(mwr::k_r_maps, dim3((r->R + 31) / 32, (r->R + 7) / 8, r->tiles), 256, 0, r->stream, r->pdl, ma));
         MW_LAUNCH_CHECK();
     }
     if (!dev) {

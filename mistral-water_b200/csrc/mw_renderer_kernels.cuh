@@ -145,6 +145,10 @@ __global__ void __launch_bounds__(3 * (N / 16)) k_r_rows(const RRowArgs a)
     const float two_pi = __fmul_rn(2.0f, MWR_PI_F);
     const uint64_t pol = evict_first_policy();  // the initial spectrum is read once per frame
     mwfft::load_twiddle_image<N, NT>(smem4, a.twimg);
+    // launched as a programmatic dependent: the phase texture (updated in place below) and the intermediate belong to the
+    // stream's earlier kernels until the predecessor has completed
+    pdl_trigger();
+    pdl_wait();
 
     auto texel = [&](float4 s, float phase_old, float rate, float kx, float ky, unsigned o, float4& F, float2& H) {
         // Dispersion.shader:37-40, GetDispersion: fmod(phase + rate * dt, 2 PI)
@@ -238,6 +242,8 @@ __global__ void __launch_bounds__(slab_w(N) * (N / 16)) k_r_cols(const RColArgs 
     const bool is_ab = (int)blockIdx.x < a.ab_blocks;
     const int b0 = is_ab ? blockIdx.x * W : ((int)blockIdx.x - a.ab_blocks) * (2 * W);
     mwfft::cpk v[16];
+    pdl_trigger();
+    pdl_wait();  // the intermediate is k_r_rows' (the predecessor in this stream)
     if (is_ab) {
         const float4* src = a.XAB + (size_t)xt * xab_tile_elems(N) + ((size_t)blockIdx.x * N + g) * W + c;
 #pragma unroll
@@ -297,6 +303,8 @@ __global__ void __launch_bounds__(256) k_r_maps(const RMapArgs a)
     const int R = a.R;
     const int x = blockIdx.x * 32 + (threadIdx.x & 31);
     const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    pdl_trigger();
+    pdl_wait();  // the two images are k_r_cols'
     if (x >= R || y >= R) return;
     const size_t base = (size_t)blockIdx.z * R * R;
     const float4* D = a.displacement + base;

@@ -85,6 +85,16 @@ class ShardedTiles:
                         for _ in range(self.nbuf)]
         self.gather = self.gathers[0]
         self._frame = 0
+        self._cur_buf = 0
+        # how the one collective is carried out: "p2p" = every rank pushes its slot straight into the peers' gather
+        # buffers over NVLink with the copy engines (CUDA IPC peer memory, no SMs taken from the frame kernels) and a
+        # 4-byte NCCL all-reduce closes the step; "nccl" = ncclAllGather.  MW_GATHER=nccl|p2p overrides.
+        self.gather_impl, self.p2p_error = "nccl", None
+        if world > 1 and self.device.type == "cuda" and make_generator is None:
+            import os
+            want = os.environ.get("MW_GATHER", "p2p")
+            if want == "p2p":
+                self._setup_p2p()
         self.rank_params = dict(resolution=N, unit_width=unit_width, choppiness=choppiness, amplitude=amplitude,
                                 wind=tile_wind(wind, self.layout.global_tile(rank, 0)),
                                 seed=base_seed + self.layout.global_tile(rank, 0), tiles=tiles_per_rank)
@@ -106,6 +116,64 @@ class ShardedTiles:
 
         return run
 
+    # ------------------------------------------------------------------ peer-memory all-gather
+    def _setup_p2p(self) -> None:
+        """Open every peer's gather buffers through CUDA IPC (one process per GPU, all GPUs of the node visible).
+        Any failure leaves gather_impl == "nccl" with the reason in p2p_error; the ranks agree on the outcome."""
+        torch = self.torch
+        import torch.distributed as dist
+
+        ok, err, peers = True, None, None
+        try:
+            from torch.multiprocessing.reductions import reduce_tensor
+
+            mine = [reduce_tensor(g) for g in self.gathers]          # (rebuild_fn, args) per buffer: picklable IPC handles
+            allh = [None] * self.world
+            dist.all_gather_object(allh, (self.device.index, mine), group=self.group)
+            peers = {}
+            for r, (dev_index, handles) in enumerate(allh):
+                if r == self.rank:
+                    continue
+                if not torch.cuda.can_device_access_peer(self.device.index, dev_index):
+                    raise RuntimeError(f"no peer access from cuda:{self.device.index} to cuda:{dev_index}")
+                peers[r] = [fn(*a) for fn, a in handles]               # tensors aliasing rank r's gather buffers
+        except Exception as e:  # noqa: BLE001
+            ok, err = False, repr(e)
+        flag = torch.tensor([1 if ok else 0], device=self.device, dtype=torch.int32)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        if int(flag.item()) == 1:
+            self.gather_impl, self._peers = "p2p", peers
+            self._push_streams = {r: torch.cuda.Stream(device=self.device) for r in peers}
+            self._push_done = {r: torch.cuda.Event() for r in peers}
+            self._token = torch.zeros(1, device=self.device, dtype=torch.int32)
+        else:
+            self.p2p_error = err or "a peer could not open the buffers"
+
+    def _push_slots(self, buf: int) -> None:
+        """Enqueue the all-gather of gather buffer `buf` on the current stream (which already waits for this rank's
+        slot to be complete and for this rank's readers of the buffer):
+          1. a 4-byte all-reduce -- every rank has reached this point, so nobody still reads what is about to be overwritten;
+          2. this rank's slot pushed into every peer's buffer, one copy-engine stream per peer, peers visited in a
+             rank-dependent order so that no destination is hit by everybody at once;
+          3. a second 4-byte all-reduce -- when it completes here, every rank's pushes have landed."""
+        torch = self.torch
+        import torch.distributed as dist
+
+        cur = torch.cuda.current_stream(self.device)
+        dist.all_reduce(self._token, group=self.group)
+        ready = torch.cuda.Event()
+        ready.record(cur)
+        src = self.gathers[buf][self.rank]
+        for i in range(1, self.world):
+            r = (self.rank + i) % self.world
+            ps = self._push_streams[r]
+            ps.wait_event(ready)
+            with torch.cuda.stream(ps):
+                self._peers[r][buf][self.rank].copy_(src, non_blocking=True)
+                self._push_done[r].record(ps)
+            cur.wait_event(self._push_done[r])
+        dist.all_reduce(self._token, group=self.group)
+
     def slot_views(self, rank: int | None = None, buf: int = 0) -> dict:
         """Field views into one rank's slot (default: ours) of gather buffer `buf`."""
         slot = self.gathers[buf][self.rank if rank is None else rank]
@@ -124,6 +192,9 @@ class ShardedTiles:
         import torch.distributed as dist
 
         if self.world == 1:
+            return
+        if self.gather_impl == "p2p":
+            self._push_slots(self._cur_buf)
             return
         dist.all_gather_into_tensor(self.gather.view(-1), self.gather[self.rank].view(-1), group=self.group)
 
@@ -149,6 +220,9 @@ class ShardedTiles:
             self._comm_used = [False, False]
         b = self._frame & 1
         self._frame += 1
+        self._cur_buf = b
+        ev_user = torch.cuda.Event()
+        ev_user.record(torch.cuda.current_stream(self.device))
         if self._comm_used[b]:
             self.stream.wait_event(self._ev_comm[b])      # buffer b is free again once its last gather is done
         self._gen(float(t), self.slot_views(buf=b))
@@ -157,7 +231,13 @@ class ShardedTiles:
         with torch.cuda.stream(self.comm_stream):
             self.comm_stream.wait_event(self._ev_gen[b])
             g = self.gathers[b]
-            dist.all_gather_into_tensor(g.view(-1), g[self.rank].view(-1), group=self.group)
+            if self.gather_impl == "p2p":
+                # peers will write into this rank's buffer b: whatever the caller enqueued so far (its reads of the frame
+                # gathered into b two calls ago) comes first
+                self.comm_stream.wait_event(ev_user)
+                self._push_slots(b)
+            else:
+                dist.all_gather_into_tensor(g.view(-1), g[self.rank].view(-1), group=self.group)
             self._ev_comm[b].record(self.comm_stream)
         self._comm_used[b] = True
         self.gather = self.gathers[b]
@@ -180,5 +260,8 @@ class ShardedTiles:
         return self.gather[r, b:e].view(self.layout.tiles_per_rank, n2, comps)[l]
 
     def close(self) -> None:
+        if getattr(self, "_peers", None):
+            self.torch.cuda.synchronize(self.device)
+            self._peers = None          # drop the IPC mappings before the owners free their buffers
         if hasattr(self, "ocean"):
             self.ocean.close()
