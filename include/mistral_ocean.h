@@ -291,6 +291,22 @@ typedef struct mw_wave_params {
 int mw_wave_displace(const mw_wave_params* p, const float* pos_xyz, float* out_xyz, float* out_nrm, int64_t n, float t,
                      void* cuda_stream);
 
+/*
+ * Multi-GPU tile sets: peer-memory plumbing for the one collective of the path, the all-gather of the
+ * final float buffers.  No reference counterpart (Scripts/FFTMesh.cs runs one mesh on one device; tiles never exchange data
+ * while being generated).  One process per GPU: every rank exports the buffer its peers write its gathered slots into,
+ * opens the peers' buffers from its own device, and pushes its slot with one asynchronous copy per peer -- copy engines over
+ * NVLink, no SMs.  Fencing between ranks is the host's business (mistral-water_b200/tiles.py uses two 4-byte NCCL all-reduces).
+ *   mw_peer_export : CUDA IPC handle of the allocation `dev_ptr` lives in + the pointer's offset inside it
+ *   mw_peer_open   : map an exported allocation for direct access from `device` (once per allocation per process)
+ *   mw_peer_copy   : asynchronous device-to-device copy on `cuda_stream` (either side may be a peer mapping)
+ */
+#define MW_PEER_HANDLE_BYTES 64
+int mw_peer_export(const void* dev_ptr, void* handle64, uint64_t* offset);
+int mw_peer_open(int device, const void* handle64, void** base);
+int mw_peer_close(int device, void* base);
+int mw_peer_copy(void* dst, const void* src, uint64_t bytes, void* cuda_stream);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

@@ -33,7 +33,9 @@ EXPORTS = (
     "mw_gerstner_displace", "mw_renderer_create", "mw_renderer_destroy", "mw_renderer_render_initial",
     "mw_renderer_set_initial", "mw_renderer_get_initial", "mw_renderer_set_phase", "mw_renderer_get_phase",
     "mw_renderer_set_params", "mw_renderer_generate_texture", "mw_renderer_sync", "mw_mesh_generate", "mw_wave_displace",
+    "mw_peer_export", "mw_peer_open", "mw_peer_close", "mw_peer_copy",
 )
+MW_PEER_HANDLE_BYTES = 64
 
 
 class MwError(RuntimeError):
@@ -142,6 +144,28 @@ def load() -> C.CDLL:
 def check(rc: int) -> None:
     if rc != MW_OK:
         raise MwError(rc, load().mw_last_error().decode("utf-8", "replace"))
+
+
+def peer_export(dev_ptr: int) -> tuple[bytes, int]:
+    """(CUDA IPC handle of the allocation dev_ptr lives in, offset of dev_ptr inside it)."""
+    h = C.create_string_buffer(MW_PEER_HANDLE_BYTES)
+    off = C.c_uint64(0)
+    check(load().mw_peer_export(C.c_void_p(dev_ptr), h, C.byref(off)))
+    return h.raw, int(off.value)
+
+
+def peer_open(device: int, handle: bytes) -> int:
+    base = C.c_void_p()
+    check(load().mw_peer_open(int(device), C.c_char_p(handle), C.byref(base)))
+    return int(base.value)
+
+
+def peer_close(device: int, base: int) -> None:
+    check(load().mw_peer_close(int(device), C.c_void_p(base)))
+
+
+def peer_copy(dst: int, src: int, nbytes: int, stream: int) -> None:
+    check(load().mw_peer_copy(C.c_void_p(dst), C.c_void_p(src), C.c_uint64(nbytes), C.c_void_p(stream)))
 
 
 def launch_count() -> int:

@@ -118,59 +118,77 @@ class ShardedTiles:
 
     # ------------------------------------------------------------------ peer-memory all-gather
     def _setup_p2p(self) -> None:
-        """Open every peer's gather buffers through CUDA IPC (one process per GPU, all GPUs of the node visible).
+        """Open every peer's gather buffers from THIS rank's device through the library's CUDA IPC entry points
+        (mw_peer_export / mw_peer_open: one process per GPU, all GPUs of the node visible, NVLink peer access).
         Any failure leaves gather_impl == "nccl" with the reason in p2p_error; the ranks agree on the outcome."""
         torch = self.torch
         import torch.distributed as dist
+        from . import native
 
-        ok, err, peers = True, None, None
+        ok, err = True, None
+        self._peer_ptr, self._peer_bases = {}, []
         try:
-            from torch.multiprocessing.reductions import reduce_tensor
-
-            mine = [reduce_tensor(g) for g in self.gathers]          # (rebuild_fn, args) per buffer: picklable IPC handles
+            mine = [native.peer_export(g.data_ptr()) for g in self.gathers]   # (64-byte IPC handle, offset) per buffer
             allh = [None] * self.world
             dist.all_gather_object(allh, (self.device.index, mine), group=self.group)
-            peers = {}
+            opened = {}
             for r, (dev_index, handles) in enumerate(allh):
                 if r == self.rank:
                     continue
                 if not torch.cuda.can_device_access_peer(self.device.index, dev_index):
                     raise RuntimeError(f"no peer access from cuda:{self.device.index} to cuda:{dev_index}")
-                peers[r] = [fn(*a) for fn, a in handles]               # tensors aliasing rank r's gather buffers
+                ptrs = []
+                for handle, off in handles:
+                    if handle not in opened:                                  # an allocation is opened once per process
+                        opened[handle] = native.peer_open(self.device.index, handle)
+                        self._peer_bases.append(opened[handle])
+                    ptrs.append(opened[handle] + off)
+                self._peer_ptr[r] = ptrs                                      # rank r's gather buffers, as seen from here
         except Exception as e:  # noqa: BLE001
             ok, err = False, repr(e)
         flag = torch.tensor([1 if ok else 0], device=self.device, dtype=torch.int32)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
         if int(flag.item()) == 1:
-            self.gather_impl, self._peers = "p2p", peers
-            self._push_streams = {r: torch.cuda.Stream(device=self.device) for r in peers}
-            self._push_done = {r: torch.cuda.Event() for r in peers}
+            self.gather_impl = "p2p"
+            self._push_streams = {r: torch.cuda.Stream(device=self.device) for r in self._peer_ptr}
+            self._push_done = {r: torch.cuda.Event() for r in self._peer_ptr}
             self._token = torch.zeros(1, device=self.device, dtype=torch.int32)
         else:
             self.p2p_error = err or "a peer could not open the buffers"
+            self._close_peers()
+
+    def _close_peers(self) -> None:
+        from . import native
+        for base in getattr(self, "_peer_bases", []):
+            try:
+                native.peer_close(self.device.index, base)
+            except Exception:  # noqa: BLE001
+                pass
+        self._peer_bases, self._peer_ptr = [], {}
 
     def _push_slots(self, buf: int) -> None:
         """Enqueue the all-gather of gather buffer `buf` on the current stream (which already waits for this rank's
         slot to be complete and for this rank's readers of the buffer):
           1. a 4-byte all-reduce -- every rank has reached this point, so nobody still reads what is about to be overwritten;
-          2. this rank's slot pushed into every peer's buffer, one copy-engine stream per peer, peers visited in a
-             rank-dependent order so that no destination is hit by everybody at once;
+          2. this rank's slot pushed into every peer's buffer (mw_peer_copy), one copy-engine stream per peer, peers
+             visited in a rank-dependent order so that no destination is hit by everybody at once;
           3. a second 4-byte all-reduce -- when it completes here, every rank's pushes have landed."""
         torch = self.torch
         import torch.distributed as dist
+        from . import native
 
         cur = torch.cuda.current_stream(self.device)
         dist.all_reduce(self._token, group=self.group)
         ready = torch.cuda.Event()
         ready.record(cur)
-        src = self.gathers[buf][self.rank]
+        slot_bytes = self.layout.slot_bytes
+        src = self.gathers[buf][self.rank].data_ptr()
         for i in range(1, self.world):
             r = (self.rank + i) % self.world
             ps = self._push_streams[r]
             ps.wait_event(ready)
-            with torch.cuda.stream(ps):
-                self._peers[r][buf][self.rank].copy_(src, non_blocking=True)
-                self._push_done[r].record(ps)
+            native.peer_copy(self._peer_ptr[r][buf] + self.rank * slot_bytes, src, slot_bytes, ps.cuda_stream)
+            self._push_done[r].record(ps)
             cur.wait_event(self._push_done[r])
         dist.all_reduce(self._token, group=self.group)
 
@@ -260,8 +278,8 @@ class ShardedTiles:
         return self.gather[r, b:e].view(self.layout.tiles_per_rank, n2, comps)[l]
 
     def close(self) -> None:
-        if getattr(self, "_peers", None):
+        if getattr(self, "_peer_bases", None):
             self.torch.cuda.synchronize(self.device)
-            self._peers = None          # drop the IPC mappings before the owners free their buffers
+            self._close_peers()         # drop the IPC mappings before the owners free their buffers
         if hasattr(self, "ocean"):
             self.ocean.close()

@@ -1,7 +1,8 @@
-timeout 300 python -m pytest tests/test_renderer_gpu.py tests/test_gerstner_gpu.py -x -q -m gpu 2>&1 | tail -3
-for v in 0 1; do echo "MW_PDL=$v"; MW_PDL=$v timeout 200 python tools/bench_extra.py --only renderer 2>&1 | python -c "
+nvidia-smi topo -m 2>&1 | head -8
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/p2p_check.py 2>&1 | tail -6
+for g in p2p nccl; do
+  MW_GATHER=$g timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 20 --warmup 3 --no-cpu-baseline --e2e-steps 2 2> gpurun_out/bench2_$g.err | tee gpurun_out/bench2_$g.json | python -c "
 import sys, json
-for l in sys.stdin:
-    try: d = json.loads(l); print(d['config'], d['us_per_frame'])
-    except Exception: pass
-"; done
+d = json.loads(sys.stdin.read().strip().splitlines()[-1]); print('$g', d['value'], d['ms_per_step'], d['multi_gpu'])"
+  tail -3 gpurun_out/bench2_$g.err
+done
