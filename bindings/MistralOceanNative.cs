@@ -127,6 +127,12 @@ namespace MistralWater.Native
         [DllImport(Lib)] public static extern int mw_wave_displace(ref MwWaveParams p, IntPtr posXyz, IntPtr outXyz, IntPtr outNrm,
             long n, float t, IntPtr cudaStream);
 
+        // multi-GPU tile sets, one process per GPU (no reference counterpart): CUDA IPC peer mappings + copy-engine pushes
+        [DllImport(Lib)] public static extern int mw_peer_export(IntPtr devPtr, byte[] handle64, out ulong offset);
+        [DllImport(Lib)] public static extern int mw_peer_open(int device, byte[] handle64, out IntPtr basePtr);
+        [DllImport(Lib)] public static extern int mw_peer_close(int device, IntPtr basePtr);
+        [DllImport(Lib)] public static extern int mw_peer_copy(IntPtr dst, IntPtr src, ulong bytes, IntPtr cudaStream);
+
         public static void Check(int rc) { if (rc != MW_OK) throw new InvalidOperationException("mistral_ocean " + rc + ": " + LastError()); }
     }
 

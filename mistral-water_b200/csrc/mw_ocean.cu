@@ -504,14 +504,27 @@ static int run_frame_n(mw_ocean* o, mwk::RowArgs ra, mwk::ColArgs ca)
     return MW_OK;
 }
 
+// pass-1 CTAs per SM asked of the compiler (__launch_bounds__ minimum blocks = the register cap) per resolution
+#ifndef MW_ROWS_RP_256
+#define MW_ROWS_RP_256 4
+#endif
+#ifndef MW_ROWS_MINB_256
+#define MW_ROWS_MINB_256 2
+#endif
+#ifndef MW_ROWS_MINB_512
+#define MW_ROWS_MINB_512 2
+#endif
+#ifndef MW_ROWS_MINB_2048
+#define MW_ROWS_MINB_2048 1
+#endif
 static int run_frame(mw_ocean* o, const mwk::RowArgs& ra, const mwk::ColArgs& ca)
 {
     switch (o->N) {
         case 32: return run_frame_n<32, 16, 1, 1>(o, ra, ca);
         case 64: return run_frame_n<64, 8, 1, 1>(o, ra, ca);
         case 128: return run_frame_n<128, 8, 1, 1>(o, ra, ca);
-        case 256: return run_frame_n<256, 4, 2, 1>(o, ra, ca);
-        case 512: return run_frame_n<512, 2, 2, 1>(o, ra, ca);
+        case 256: return run_frame_n<256, MW_ROWS_RP_256, MW_ROWS_MINB_256, 1>(o, ra, ca);
+        case 512: return run_frame_n<512, 2, MW_ROWS_MINB_512, 1>(o, ra, ca);
         case 1024: {
             static const int minb = getenv("MW_ROWS_MINB") ? atoi(getenv("MW_ROWS_MINB")) : 3;
             constexpr int CM = MW_SLABW_1024 == 4 ? 2 : 1;
@@ -521,7 +534,7 @@ static int run_frame(mw_ocean* o, const mwk::RowArgs& ra, const mwk::ColArgs& ca
             return minb == 3 ? run_frame_n<1024, 1, 3, CM>(o, ra, ca) : run_frame_n<1024, 1, 4, CM>(o, ra, ca);
 #endif
         }
-        case 2048: return run_frame_n<2048, 1, 1, 1>(o, ra, ca);
+        case 2048: return run_frame_n<2048, 1, MW_ROWS_MINB_2048, 1>(o, ra, ca);
     }
     mw_set_error("unsupported resolution %d", o->N);
     return MW_E_INVALID_ARG;

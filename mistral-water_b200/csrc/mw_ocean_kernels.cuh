@@ -515,9 +515,26 @@ __device__ __forceinline__ float rsqrt_ftz(float x)  // argument >= 1 here: no d
 // OUTS: which (A,B)-slab outputs exist, as a compile-time set (bit 0 hds, 1 normal, 2 whitecap, 3 Jacobian) so that the
 // extraction is straight-line code; OUTS = -1 decides per pointer at run time (any other combination).
 __host__ __device__ constexpr int nstage_slots(int N) { return N >= 256 ? MW_NSTAGE : 1; }
+// Register cap per resolution = what decides the CTAs per SM of this kernel ((W + 1) N / 16 threads per CTA):
+// N = 1024: 576 threads, one CTA per SM either way; N = 512: 288 threads, 112 registers let two CTAs share an SM
+// (128 leaves one); N = 256: 144 threads, 96 registers -> four CTAs (the shared-memory limit) instead of three.
+#ifndef MW_COLS_MAXREG_512
+#define MW_COLS_MAXREG_512 128
+#endif
+#ifndef MW_COLS_MAXREG_256
+#define MW_COLS_MAXREG_256 128
+#endif
+__host__ __device__ constexpr int cols_maxreg(int N)
+{
+    return fft_pts(N) == 32 ? 168
+         : N == 1024 ? (MW_SLABW_1024 == 8 ? MW_COLS_MAXREG : 96)
+         : N == 512 ? MW_COLS_MAXREG_512
+         : N == 256 ? MW_COLS_MAXREG_256
+         : 128;
+}
 template <int N, int MINB, int OUTS>
 __global__ void __launch_bounds__((slab_w(N) + 1) * (N / fft_pts(N)), MINB)
-__maxnreg__(fft_pts(N) == 32 ? 168 : (N == 1024 ? (MW_SLABW_1024 == 8 ? MW_COLS_MAXREG : 96) : 128)) k_cols_extract(const __grid_constant__ ColArgs a)
+__maxnreg__(cols_maxreg(N)) k_cols_extract(const __grid_constant__ ColArgs a)
 {
     constexpr int NS = nstage_slots(N);
     constexpr int PTS = fft_pts(N);
