@@ -71,6 +71,18 @@ def test_null_arguments_are_errors_not_crashes(mw):
     assert lib.mw_fft2d(0, 48, 1, -1, x.ctypes.data, x.ctypes.data) == mw.native.MW_E_INVALID_ARG
     assert lib.mw_gerstner_displace(None, None, None, None, 0, 0.0, None) == mw.native.MW_E_INVALID_ARG
     lib.mw_ocean_destroy(None)  # no-op
+    # peer-memory entry points of the multi-GPU tile set
+    import ctypes as C
+    h = C.create_string_buffer(mw.native.MW_PEER_HANDLE_BYTES)
+    off = C.c_uint64(0)
+    base = C.c_void_p()
+    assert lib.mw_peer_export(None, h, C.byref(off)) == mw.native.MW_E_INVALID_ARG
+    assert lib.mw_peer_export(C.c_void_p(4096), None, C.byref(off)) == mw.native.MW_E_INVALID_ARG
+    assert lib.mw_peer_open(0, None, C.byref(base)) == mw.native.MW_E_INVALID_ARG
+    assert lib.mw_peer_open(0, h, None) == mw.native.MW_E_INVALID_ARG
+    assert lib.mw_peer_copy(None, None, C.c_uint64(16), None) == mw.native.MW_E_INVALID_ARG
+    assert lib.mw_peer_close(0, None) == mw.native.MW_OK  # nothing to close
+    assert b"mw_peer" in lib.mw_last_error()
 
 
 def test_no_cpu_fallback_without_a_device(mw):
