@@ -104,6 +104,21 @@ def cpu_reference_rate(N, seed, vertices, threads, t=1.7):
     return vertices / dt, dt
 
 
+def cpu_fft_form_rate(N, seed, t=1.7):
+    """The same frame on the CPU in TRANSFORM form (oracle/ref_fft64.py: numpy fp64, five ifft2 + the extraction of
+    FFTMesh.cs:243-276), one thread: separates what the algorithm buys (O(N^2 log N) instead of the reference's
+    O(N^4)) from what the hardware buys.  Not what the reference does -- labelled as such in the JSON line."""
+    from oracle import cref, ref_fft64
+
+    p = cref.params(N)
+    _, h0, hc = cref.generate_mesh(p, seed=seed)
+    ref_fft64.evaluate_waves(h0, hc, N, p.length, p.unit_width, p.choppiness, 0.0)  # warm-up (FFT plans, page faults)
+    t0 = time.perf_counter()
+    ref_fft64.evaluate_waves(h0, hc, N, p.length, p.unit_width, p.choppiness, t)
+    dt = time.perf_counter() - t0
+    return N * N / dt, dt
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -339,6 +354,13 @@ def run_engine(args):
                "sample": f"{verts} of {N * N} vertices of the same {N}x{N} grid through the literal "
                          f"FFTMesh.Displacement loop (oracle/ref_fftmesh.c), 1 thread as Unity runs it; {dt:.1f} s",
                "host_threads_available": len(os.sched_getaffinity(0))}
+        try:
+            frate, fdt = cpu_fft_form_rate(N, 1000)
+            cpu["fft_form"] = {"value": frate, "unit": UNIT, "cores": 1, "kind": "port, transform form -- NOT what the reference "
+                               "does (it evaluates the O(N^4) direct sum above)",
+                               "sample": f"one full {N}x{N} frame: numpy fp64 ifft2 x 5 + extraction (oracle/ref_fft64.py), {fdt:.2f} s"}
+        except Exception as e:  # noqa: BLE001
+            cpu["fft_form"] = {"error": repr(e)}
 
     if rank == 0:
         line = {
