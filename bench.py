@@ -186,7 +186,12 @@ def run_engine(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # MW_NCCL_HIGH_PRIORITY=1 (experiment, off by default): NCCL's stream gets scheduling priority over the frame kernels,
+        # so that the 4-byte fences of the peer-memory gather do not wait for an SM behind a frame
+        opts = None
+        if os.environ.get("MW_NCCL_HIGH_PRIORITY", "0") == "1":
+            opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+        dist.init_process_group("nccl", device_id=dev, pg_options=opts)
     N, T, K, W = args.resolution, args.tiles, args.steps, max(args.warmup, 3)
     pts_rank = T * N * N
     peak, peak_src = peaks()
