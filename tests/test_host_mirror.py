@@ -76,3 +76,17 @@ def test_tile_layout_and_wind_rotation(mw):
     w = tile_wind((5.0, 3.0), 2)  # 90 degrees
     assert np.allclose(w, (-3.0, 5.0))
     assert np.allclose(np.hypot(*tile_wind((5.0, 3.0), 5)), np.hypot(5.0, 3.0))
+
+
+def test_bench_helpers_run_without_a_gpu(cref):
+    """bench.py's CPU-side pieces: the transform-form CPU figure and the workload description of both gather arms."""
+    import argparse
+    import bench
+
+    rate, dt = bench.cpu_fft_form_rate(64, 1234)
+    assert rate > 0 and dt > 0
+    args = argparse.Namespace(resolution=1024, tiles=16)
+    one = bench.workload_config(args, 1)
+    assert one["collective"] == "none" and one["algorithmic_bytes_per_point"] == 44 and one["parallelism"] == "tiles1"
+    assert "peer memory" in bench.workload_config(args, 8, "p2p")["collective"]
+    assert "NCCL" in bench.workload_config(args, 8, "nccl")["collective"]
