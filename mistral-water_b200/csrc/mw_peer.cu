@@ -5,6 +5,8 @@
 // the peers' buffers FROM ITS OWN DEVICE (cudaIpcMemLazyEnablePeerAccess maps the exporter's memory for direct NVLink
 // access by the opening device), and the all-gather of the final float buffers becomes one asynchronous copy per
 // peer: the copy engines move the slot over NVLink / NVSwitch while the SMs run the next frame.
+#include <string.h>
+
 #include "mw_common.cuh"
 
 extern "C" int mw_peer_export(const void* dev_ptr, void* handle64, uint64_t* offset)
