@@ -1,13 +1,16 @@
 #!/usr/bin/env python
 """bench.py -- the hot-path benchmark (driver contract: one JSON line on stdout from rank 0).
 
-Workload (BASELINE.json configs[2], the one the metric's "disp+Jacobian" is quoted on):
-    one step = one frame of a batch of TILES independent 1024 x 1024 Tessendorf grids, each
+N = 1 (BASELINE.json configs[2], the one the metric's "disp+Jacobian" is quoted on):
+    one step = one frame of a batch of 16 independent 1024 x 1024 Tessendorf grids, each
     h0 -> h(k,t) -> 2-D IFFT -> height + hds + normal + Jacobian whitecap (44 algorithmic B/point),
-    outputs left in HBM.  TILES = 16 makes the per-step input (268 MB) and output (470 MB) larger
+    outputs left in HBM.  16 tiles make the per-step input (268 MB) and output (470 MB) larger
     than the 126 MB L2, so no flush is needed between timed steps.
-With --gpus N > 1 (torchrun, one rank per GPU, NCCL) every rank runs the same batch (weak scaling) and
-the step ends with the path's one collective: the in-place all-gather of the final float buffers.
+N > 1 (torchrun, one rank per GPU; BASELINE.json configs[4]):
+    every rank generates ONE 2048 x 2048 tile (seed 1000 + rank, wind rotated 45 deg * rank) and the step
+    ends with the path's one collective, the in-place all-gather of the final float buffers
+    (117.4 MB per rank), through the mw_tiles_* C ABI: peer-memory pushes (default arm) and ncclAllGather
+    (second arm, reported beside it).  Every rank issues exactly the same sequence of collective calls.
 
     python bench.py [--gpus N] [--steps K] [--warmup W]          # the CUDA engine
     python bench.py --impl reference [...]                       # the reference's CPU algorithm (oracle port)
@@ -27,7 +30,8 @@ sys.path.insert(0, ROOT)
 METRIC = "grid-points/sec (spectrum→IFFT→disp+Jacobian) at N×N; achieved HBM GB/s"
 UNIT = "grid-points/s"
 ALG_BYTES_PIPELINE = 44  # read h0+h0conj 16, write height 4 + hds 8 + normal 12 + whitecap 4
-ALG_BYTES_KERNEL = {"spectrum_rows": 16 + 24, "cols_extract": 24 + 28}  # + the 24 B/pt intermediate
+ALG_BYTES_KERNEL = {"spectrum_rows": 16 + 24, "cols_extract": 24 + 28}  # a kernel's own bytes: + the 24 B/pt intermediate
+NVLINK_NOMINAL_GBS, NVLINK_PEER_COPY_GBS = 900.0, 770.0   # per direction per GPU: nominal / measured peer copy (B200_PROFILING.md)
 
 
 def peaks():
@@ -119,10 +123,21 @@ def cpu_fft_form_rate(N, seed, t=1.7):
     return N * N / dt, dt
 
 
+def defaults_for_world(args, world):
+    """N = 1: configs[2] batched (16 x 1024^2).  N > 1: configs[4] (one 2048^2 tile per GPU)."""
+    if args.resolution is None:
+        args.resolution = 1024 if world == 1 else 2048
+    if args.tiles is None:
+        args.tiles = 16 if world == 1 else 1
+    return args
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
+    defaults_for_world(args, world)
     from oracle import cref
     cref.build()
     N = args.resolution
@@ -145,7 +160,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_t / max(args.steps, 1),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, 1),
+        "config": workload_config(args, world),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -153,25 +168,122 @@ def run_reference(args):
     emit(line)
 
 
-def workload_config(args, world, gather_impl="nccl"):
+def workload_config(args, world, gather_impl="peer"):
     N, T = args.resolution, args.tiles
-    coll = ("one in-place all-gather of the final float buffers per step, over NVLink peer memory: every rank's copy engines "
-            "push its slot into the peers' buffers (CUDA IPC), two 4-byte NCCL all-reduces fence the step"
-            if gather_impl == "p2p" else "one in-place all-gather of the final float buffers (NCCL) per step")
+    if world == 1:
+        name = (f"{T} x ({N}x{N} Tessendorf grid, height+hds+normal+Jacobian whitecap) per step"
+                + (" = BASELINE configs[2] batched" if N == 1024 else ""))
+        coll = "none"
+    else:
+        name = (f"{world} x {T} independent {N}x{N} ocean tiles, {T} per GPU (seed 1000+tile, wind rotated 45 deg per rank), "
+                f"all-gather of the final float buffers ({T * N * N * 28 / 1e6:.1f} MB per rank)"
+                + (" = BASELINE configs[4]" if (N, T) == (2048, 1) else ""))
+        coll = ("one in-place all-gather of the final float buffers per step over NVLink peer memory: every rank's copy engines "
+                "push its slot into the peers' buffers (CUDA IPC mappings), fenced by stream memory operations on peer flag "
+                "words (cuStreamWriteValue32 / cuStreamWaitValue32) -- no kernel, no SM; the ncclAllGather arm is reported under multi_gpu"
+                if gather_impl in ("peer", "p2p") else "one in-place ncclAllGather of the final float buffers per step")
     return {
-        "workload": f"{T} x ({N}x{N} Tessendorf grid, height+hds+normal+Jacobian whitecap) per GPU per step "
-                    f"= BASELINE configs[2] batched",
+        "workload": name,
         "resolution": N, "tiles_per_gpu": T, "points_per_step_per_gpu": T * N * N,
         "outputs": "height,hds,normal,whitecap (28 B/pt)", "algorithmic_bytes_per_point": ALG_BYTES_PIPELINE,
         "l2": f"inputs {T * N * N * 16 / 1e6:.0f} MB + outputs {T * N * N * 28 / 1e6:.0f} MB per step > 126 MB L2; no flush",
-        "collective": "none" if world == 1 else coll,
+        "collective": coll,
         "parallelism": f"tiles{world}",
     }
 
 
+# ----------------------------------------------------------------------------- the other BASELINE configs (rank 0, N = 1)
+def extra_configs(mw, torch, stream, peak):
+    """Driver-visible lines for BASELINE configs 1, 2, 4 (Gerstner), the single 1024^2 frame and the 2048^2 tile:
+    CUDA events on the launching stream, 10 warm-up frames.  Single small frames fit L2: latency numbers, labelled."""
+    out = {}
+    comps = {"height": 1, "disp": 2, "normal": 3, "whitecap": 1}
+
+    def ocean(key, N, tiles, names, K):
+        o = mw.Ocean(N, seed=1234 if N <= 256 else 1000, tiles=tiles, device_ptrs=True)
+        o.set_stream(stream.cuda_stream)
+        o.init_spectrum()
+        n2 = N * N * tiles
+        bufs = {k: torch.empty(n2 * comps[k], device="cuda") for k in names}
+        bpp = 16 + 4 * sum(comps[k] for k in names)
+        with torch.cuda.stream(stream):
+            for i in range(10):
+                o.generate(0.016 * i, bufs)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for i in range(K):
+                o.generate(0.016 * i, bufs)
+            e1.record(stream)
+            torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / K
+        o.close()
+        fits = n2 * (bpp + 24) < 100e6
+        out[key] = {"resolution": N, "tiles_per_call": tiles, "outputs": list(names), "us_per_frame": round(ms * 1e3, 2),
+                    "value": n2 / ms * 1e3, "unit": UNIT, "algorithmic_bytes_per_point": bpp,
+                    "achieved_gbs": round(n2 * bpp / ms / 1e6, 1), "frac_of_hbm_peak": round(n2 * bpp / ms / 1e6 / peak, 4),
+                    "l2": "working set fits the 126 MB L2: a latency figure, not an HBM figure" if fits else "working set exceeds L2"}
+
+    all4, hdn = ("height", "disp", "normal", "whitecap"), ("height", "disp", "normal")
+    ocean("config1_64x64_single_frame", 64, 1, all4, 200)
+    ocean("config2_256x256_single_frame", 256, 1, hdn, 200)
+    ocean("config2_256x256_x256_per_call", 256, 256, hdn, 20)
+    ocean("config3_1024x1024_single_frame", 1024, 1, all4, 200)
+    ocean("config5_one_2048x2048_tile", 2048, 1, all4, 50)
+    ocean("config5_four_2048x2048_tiles", 2048, 4, all4, 20)
+    # config 4: Gerstner 32 waves x 1M vertices, L2 flushed between iterations (the 24 MB working set would sit in L2)
+    N = 1024
+    g = mw.pond_wave_table_32(device_ptrs=True)
+    ax = torch.arange(N, device="cuda", dtype=torch.float32) - N // 2 + 0.5
+    pos = torch.zeros(N * N, 3, device="cuda")
+    pos[:, 0] = ax.repeat_interleave(N)
+    pos[:, 2] = ax.repeat(N)
+    res = torch.empty_like(pos)
+    flush = torch.empty(64 << 20, device="cuda")
+    with torch.cuda.stream(stream):
+        for i in range(5):
+            g.displace(pos, 1.7, out=res, stream=stream.cuda_stream)
+        torch.cuda.synchronize()
+        tot, K = 0.0, 30
+        for i in range(K):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            g.displace(pos, 1.7 + 0.016 * i, out=res, stream=stream.cuda_stream)
+            e1.record(stream)
+            torch.cuda.synchronize()
+            tot += e0.elapsed_time(e1)
+    ms = tot / K
+    out["config4_gerstner_32_waves_1M_vertices"] = {
+        "us": round(ms * 1e3, 2), "value": N * N / ms * 1e3, "unit": "vertices/s", "algorithmic_bytes_per_vertex": 24,
+        "achieved_gbs": round(N * N * 24 / ms / 1e6, 1), "frac_of_hbm_peak": round(N * N * 24 / ms / 1e6 / peak, 4),
+        "l2": "flushed between iterations (256 MB memset)",
+        "bound": "MUFU/FP32 issue (64 transcendentals per vertex at 24 B/vertex), not HBM: profiles/ has the pipe utilisation"}
+    return out
+
+
+def bind_to_gpu_numa(index):
+    """Best effort: run this rank on the CPUs NVML names as local to its GPU, so that its pinned host buffers are first
+    touched on that NUMA node (round 1: per-rank e2e degraded 9.8 -> 49 ms at 8 ranks with every rank on CPUs 0-31)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        ncpu = os.cpu_count() or 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        ideal = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        use = ideal & allowed
+        if not use:
+            return {"bound": False, "why": "the GPU's local CPUs are outside this process' allowed set", "allowed": len(allowed)}
+        os.sched_setaffinity(0, use)
+        return {"bound": True, "cpus": len(use), "first_cpu": min(use)}
+    except Exception as e:  # noqa: BLE001
+        return {"bound": False, "why": repr(e)}
+
+
 # ----------------------------------------------------------------------------- the CUDA engine arm
 def run_engine(args):
-    import numpy as np
     import torch
     import torch.distributed as dist
 
@@ -185,19 +297,14 @@ def run_engine(args):
         raise SystemExit("bench.py: no CUDA device -- the engine has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_to_gpu_numa(local) if world > 1 else None     # before any pinned allocation: first touch decides the node
     if world > 1:
-        # MW_NCCL_HIGH_PRIORITY=1 (experiment, off by default): NCCL's stream gets scheduling priority over the frame kernels,
-        # so that the 4-byte fences of the peer-memory gather do not wait for an SM behind a frame
-        opts = None
-        if os.environ.get("MW_NCCL_HIGH_PRIORITY", "0") == "1":
-            opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
-        dist.init_process_group("nccl", device_id=dev, pg_options=opts)
+        dist.init_process_group("nccl", device_id=dev)
+    defaults_for_world(args, world)
     N, T, K, W = args.resolution, args.tiles, args.steps, max(args.warmup, 3)
     pts_rank = T * N * N
     peak, peak_src = peaks()
-
-    st = ShardedTiles(N, rank, world, tiles_per_rank=T, base_seed=1000, device=dev)
-    ocean, stream = st.ocean, st.stream
+    slot_bytes = pts_rank * 28
 
     def barrier():
         torch.cuda.synchronize()
@@ -205,76 +312,95 @@ def run_engine(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step(k):
-        # N = 1: the engine's kernels on `stream`.  N > 1: the same, then the path's one collective -- the
-        # all-gather of frame k runs on a communication stream under the generation of frame k + 1
+    def max_over_ranks(x):
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
         if world > 1:
-            st.generate_pipelined(0.016 * k)
-        else:
-            st.generate_local(0.016 * k)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
-    with torch.cuda.stream(stream):
-        for k in range(W):
-            step(k)
-        st.finish()
+    def timed(st, fn, n, finish=True):
+        """n calls of fn(k) between two CUDA events on the user stream; every rank makes the same calls."""
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        launches0 = mw.native.launch_count()
-        with ClockSampler(local) as clk:
-            e0.record(stream)
-            for k in range(K):
-                step(W + k)
-            st.finish()          # (N > 1) the last gathers are inside the timed region
-            e1.record(stream)
+        e0.record(st.stream)
+        for k in range(n):
+            fn(k)
+        if finish:
+            st.finish()
+        e1.record(st.stream)
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1))
+
+    def measure_arm(gather):
+        """One gather arm at world > 1 (or the plain engine at world == 1): the timed step, then compute alone and the
+        gather alone.  Rank-uniform control flow throughout: K, W and the leg order are the same on every rank."""
+        st = ShardedTiles(N, rank, world, tiles_per_rank=T, base_seed=1000, device=dev, gather=gather)
+        step = (lambda k: st.generate_pipelined(0.016 * k)) if world > 1 else (lambda k: st.generate_local(0.016 * k))
+        res = {"impl": st.gather_impl}
+        with torch.cuda.stream(st.stream):
+            for k in range(W):
+                step(k)
+            st.finish()
             barrier()
-            ms = e0.elapsed_time(e1)
-            launches = mw.native.launch_count() - launches0
-            # a short timed region gives the sampler too few looks: keep the same load running untimed
-            extra = 0
-            while len(clk.samples) < 8 and extra < 200:
-                for k in range(8):
-                    step(k)
+            launches0 = mw.native.launch_count()
+            with ClockSampler(local) as clk:
+                res["ms"] = timed(st, lambda k: step(W + k), K)
+                res["launches"] = mw.native.launch_count() - launches0
+                # a short timed region gives the sampler too few looks: keep the SAME KERNELS running untimed -- compute
+                # only (generate_local has no collective), so a rank-local number of extra iterations cannot desynchronise
+                # the ranks
+                extra = 0
+                while len(clk.samples) < 8 and extra < 200:
+                    for k in range(8):
+                        st.generate_local(0.016 * k)
+                    st.finish()
+                    torch.cuda.synchronize()
+                    extra += 1
+            res["clocks"] = clk.summary()
+            res["clocks"]["sampled"] = "timed region" + (f" + {extra * 8} untimed compute-only steps of the same kernels" if extra else "")
+            res["compute_ms"] = res["ms"]
+            res["gather_ms"] = 0.0
+            if world > 1:
+                res["compute_ms"] = timed(st, lambda k: st.generate_local(0.016 * k), K)
+                st.generate_local(0.0)
                 st.finish()
-                torch.cuda.synchronize()
-                extra += 1
-        clocks = clk.summary()
-        clocks["sampled"] = "timed region" + (f" + {extra * 8} untimed steps of the same load" if extra else "")
-        tms = torch.tensor([ms], device=dev)
-        if world > 1:
-            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-        ms = float(tms.item())
+                res["gather_ms"] = timed(st, lambda k: st.all_gather(), K)
+        st.sync()
+        return st, res
 
-        # compute-only time (no collective), same loop
-        compute_ms = ms
-        gather_ms = 0.0
-        if world > 1:
-            barrier()
-            e0.record(stream)
-            for k in range(K):
-                st.generate_local(0.016 * k)
-            e1.record(stream)
-            barrier()
-            t2 = torch.tensor([e0.elapsed_time(e1)], device=dev)
-            dist.all_reduce(t2, op=dist.ReduceOp.MAX)
-            compute_ms = float(t2.item())
-            e0.record(stream)
-            for k in range(K):
-                st.all_gather()
-            e1.record(stream)
-            barrier()
-            t3 = torch.tensor([e0.elapsed_time(e1)], device=dev)
-            dist.all_reduce(t3, op=dist.ReduceOp.MAX)
-            gather_ms = float(t3.item())
-
+    st, main = measure_arm("peer")
+    ms, compute_ms, clocks, launches = main["ms"], main["compute_ms"], main["clocks"], main["launches"]
     value = world * pts_rank * K / (ms * 1e-3)
+    stream = st.stream
 
-    # ---- per-kernel durations, live, with CUDA events on the launching stream (MW_PROFILE handle) ----
+    # ---- roofline: the SURVEY 8(d) figure -- 44 algorithmic B/pt x points per step / step time of the timed region ----
     roof = None
     if rank == 0:
+        frame_ms = compute_ms / K
+        ach = ALG_BYTES_PIPELINE * pts_rank / (frame_ms * 1e-3) / 1e9
+        roof = {
+            "bound": "hbm", "kernel": "k_spectrum_rows + k_cols_extract (one frame = one mw_ocean_generate)",
+            "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4), "traffic": None,
+            "peak_source": peak_src, "algorithmic_bytes_per_point": ALG_BYTES_PIPELINE, "points_per_step": pts_rank,
+            "algorithmic_bytes_per_step": ALG_BYTES_PIPELINE * pts_rank,
+            "timing": "CUDA events on the launching stream around the K timed steps (compute only), max over ranks",
+        }
+        tr = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tr):
+            try:
+                t = json.load(open(tr)).get(f"{N}x{T}")
+                if t:
+                    roof["traffic"] = t["dram_bytes_per_step"]
+                    roof["traffic_over_algorithmic"] = round(t["dram_bytes_per_step"] / (ALG_BYTES_PIPELINE * pts_rank), 3)
+                    roof["traffic_source"] = t["source"]
+            except Exception:  # noqa: BLE001
+                pass
+        # per-kernel durations, live, with CUDA events on the launching stream (MW_PROFILE handle: single stream, so the
+        # launches do not overlap -- shares of the step, not timings of the timed region)
         prof = mw.Ocean(N, seed=1000, tiles=T, device=local, device_ptrs=True, profile=True)
         prof.set_stream(stream.cuda_stream)
         prof.init_spectrum()
-        views = st.slot_views()
+        views = {k: torch.empty(pts_rank * c, device=dev) for k, c in FIELDS}
         with torch.cuda.stream(stream):
             for k in range(3):
                 prof.generate(0.016 * k, views)
@@ -284,108 +410,167 @@ def run_engine(args):
                 prof.generate(0.016 * k, views)
             kms, kn = prof.kernel_times()
         prof.close()
+        del views
         names = ["spectrum_rows", "cols_extract"]
-        per = {names[i]: kms[i] / max(kn[i], 1) for i in range(2)}              # average duration of ONE launch
-        per_step = {names[i]: kms[i] / K for i in range(2)}                      # kernel time per step (all its launches)
-        launches_per_step = {names[i]: kn[i] / K for i in range(2)}
-        dom = max(per_step, key=per_step.get)
-        pts_per_launch = pts_rank / launches_per_step[dom]                       # the engine issues the batch tile group by tile group
-        ach = ALG_BYTES_KERNEL[dom] * pts_per_launch / (per[dom] * 1e-3) / 1e9
-        frame_ms = compute_ms / K
-        roof = {
-            "bound": "hbm", "kernel": "k_" + dom, "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
-            "frac": round(ach / peak, 4), "traffic": None, "peak_source": peak_src,
-            "algorithmic_bytes_per_point": ALG_BYTES_KERNEL[dom], "points_per_launch": int(pts_per_launch),
-            "launches_per_step": launches_per_step,
-            "avg_launch_ms": {k: round(v, 4) for k, v in per.items()},
-            "share_of_step": {k: round(v / sum(per_step.values()), 3) for k, v in per_step.items()},
-            "timing": "CUDA events around every launch on the launching stream (MW_PROFILE handle, single stream, no overlap "
-                      "between launches), same K steps as the timed region",
-            "pipeline": {"algorithmic_bytes_per_point": ALG_BYTES_PIPELINE,
-                         "achieved": round(ALG_BYTES_PIPELINE * pts_rank / (frame_ms * 1e-3) / 1e9, 1),
-                         "frac": round(ALG_BYTES_PIPELINE * pts_rank / (frame_ms * 1e-3) / 1e9 / peak, 4),
-                         "note": "44 B/pt x points per step / whole-step time of the timed region (both kernels, two streams overlapped)"},
-        }
-        tr = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tr):
-            try:
-                t = json.load(open(tr)).get("k_" + dom)
-                if t:
-                    roof["traffic"] = t["bytes_per_tile"] * pts_per_launch / (N * N)
-                    roof["traffic_source"] = t["source"]
-            except Exception:  # noqa: BLE001
-                pass
+        per = {names[i]: kms[i] / max(kn[i], 1) for i in range(2)}
+        per_step = {names[i]: kms[i] / K for i in range(2)}
+        lps = {names[i]: kn[i] / K for i in range(2)}
+        roof["kernels"] = {
+            "k_" + nm: {"avg_launch_ms": round(per[nm], 4), "launches_per_step": lps[nm],
+                        "share_of_step": round(per_step[nm] / sum(per_step.values()), 3),
+                        "own_bytes_per_point": ALG_BYTES_KERNEL[nm],
+                        "own_gbs": round(ALG_BYTES_KERNEL[nm] * pts_rank / lps[nm] / (per[nm] * 1e-3) / 1e9, 1)}
+            for nm in names}
+        roof["kernels"]["note"] = ("serialised on one stream (MW_PROFILE); own_bytes include the 24 B/pt intermediate the kernel "
+                                   "itself moves (L2-resident in the timed scheduling) -- sub-figures, not the roofline fraction")
 
-    # ---- end to end through the C ABI with HOST buffers (what the C# host calls) ----
-    Ke = max(1, min(K, args.e2e_steps))
-    # MW_HOST_ASYNC: calls enqueue and return; results leave on the handle's copy stream, so the upload of step k + 1
-    # overlaps the download of step k (PCIe is full duplex); everything is complete at host.sync()
-    host = mw.Ocean(N, seed=1000 + rank * T, tiles=T, device=local, host_async=True)
-    pin = lambda *shape: torch.empty(*shape, dtype=torch.float32).pin_memory()  # noqa: E731
-    h0, h0c = pin(pts_rank, 2), pin(pts_rank, 2)
-    host.init_spectrum()
-    host.get_h0_into(h0, h0c)
-    outs = {name: pin(pts_rank, c) for name, c in FIELDS}
-    for k in range(2):
-        host.set_h0(h0, h0c)
-        host.generate(0.016 * k, outs)
-    host.sync()
-    barrier()
-    t0 = time.perf_counter()
-    for k in range(Ke):
-        host.set_h0(h0, h0c)                 # verttilde / vertConj from host memory, every call
-        host.generate(0.016 * k, outs)       # results land in host arrays (complete at sync)
-    host.sync()
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], device=dev)
+    # ---- the NCCL arm beside the default one (world > 1): same legs, same call counts on every rank ----
+    nccl = None
     if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_s = float(te.item())
-    checksum = float(outs["height"][: N * N].double().abs().sum())
-    host.close()
-    e2e = {"value": world * pts_rank * Ke / e2e_s, "unit": UNIT, "h2d_bytes_per_step": pts_rank * 16,
-           "d2h_bytes_per_step": pts_rank * 28, "steps": Ke, "ms_per_step": 1e3 * e2e_s / Ke,
-           "api": "mw_ocean_set_h0 + mw_ocean_generate with pinned host buffers on an MW_HOST_ASYNC handle (upload of step k+1 overlaps download of step k), mw_ocean_sync at the end", "height_abs_sum_tile0": checksum}
+        st.close()
+        barrier()
+        st2, nccl = measure_arm("nccl")
+        st2.close()
+        barrier()
+        st, _ = None, None
 
-    # ---- CPU baseline beside it (rank 0, N = 1 only; bounded sample) ----
+    # ---- end to end through the C ABI with HOST buffers ----
+    Ke = max(1, min(K, args.e2e_steps))
+    pin = lambda *shape: torch.empty(*shape, dtype=torch.float32).pin_memory()  # noqa: E731
+    if world == 1:
+        # what the C# host calls: mw_ocean_set_h0 + mw_ocean_generate on pinned host arrays.  MW_HOST_ASYNC: calls enqueue and
+        # return; results leave on the handle's copy stream, so the upload of step k + 1 overlaps the download of step k
+        host = mw.Ocean(N, seed=1000, tiles=T, device=local, host_async=True)
+        h0, h0c = pin(pts_rank, 2), pin(pts_rank, 2)
+        host.init_spectrum()
+        host.get_h0_into(h0, h0c)
+        outs = {name: pin(pts_rank, c) for name, c in FIELDS}
+        for k in range(2):
+            host.set_h0(h0, h0c)
+            host.generate(0.016 * k, outs)
+        host.sync()
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(Ke):
+            host.set_h0(h0, h0c)                 # verttilde / vertConj from host memory, every call
+            host.generate(0.016 * k, outs)       # results land in host arrays (complete at sync)
+        host.sync()
+        torch.cuda.synchronize()
+        e2e_s = max_over_ranks(time.perf_counter() - t0)
+        checksum = float(outs["height"][: N * N].double().abs().sum())
+        host.close()
+        e2e = {"value": world * pts_rank * Ke / e2e_s, "unit": UNIT, "h2d_bytes_per_step": pts_rank * 16,
+               "d2h_bytes_per_step": pts_rank * 28, "steps": Ke, "ms_per_step": 1e3 * e2e_s / Ke,
+               "api": "mw_ocean_set_h0 + mw_ocean_generate with pinned host buffers on an MW_HOST_ASYNC handle (upload of step "
+                      "k+1 overlaps download of step k), mw_ocean_sync at the end", "height_abs_sum_tile0": checksum}
+    else:
+        # the tile set: every step uploads this rank's h0 from pinned host memory, generates, ALL-GATHERS, and downloads this
+        # rank's slot of the gathered buffer once the gather has completed (the hosts fetch each tile once, over N PCIe links)
+        st3 = ShardedTiles(N, rank, world, tiles_per_rank=T, base_seed=1000, device=dev, gather="peer")
+        ts = st3.tileset
+        h0, h0c = pin(pts_rank, 2), pin(pts_rank, 2)
+        d_h0, d_h0c = torch.empty(pts_rank, 2, device=dev), torch.empty(pts_rank, 2, device=dev)
+        lib = mw.native.load()
+        mw.native.check(lib.mw_ocean_get_h0(ts.ocean_handle(0), d_h0.data_ptr(), d_h0c.data_ptr()))
+        ts.sync()
+        h0.copy_(d_h0)
+        h0c.copy_(d_h0c)
+        out_host = pin(pts_rank * 7)
+
+        d2h = torch.cuda.Stream(device=dev)
+        ev_gathered = [torch.cuda.Event(), torch.cuda.Event()]
+        ev_fetched = [torch.cuda.Event(), torch.cuda.Event()]
+
+        def e2e_step(k):
+            b = k & 1
+            if k >= 2:
+                st3.stream.wait_event(ev_fetched[b])          # buffer b is rewritten by this frame: its download comes first
+            d_h0.copy_(h0, non_blocking=True)
+            d_h0c.copy_(h0c, non_blocking=True)
+            ts.set_h0(0, d_h0.data_ptr(), d_h0c.data_ptr())
+            g = st3.generate_pipelined(0.016 * k)
+            st3.finish()                                      # the user stream waits for this frame's gather
+            ev_gathered[b].record(st3.stream)
+            d2h.wait_event(ev_gathered[b])
+            with torch.cuda.stream(d2h):                      # results leave on a copy stream, under the next step's upload
+                out_host.copy_(g[rank], non_blocking=True)
+                ev_fetched[b].record(d2h)
+
+        with torch.cuda.stream(st3.stream):
+            for k in range(2):
+                e2e_step(k)
+            d2h.synchronize()
+            barrier()
+            t0 = time.perf_counter()
+            for k in range(Ke):
+                e2e_step(2 + k)
+            st3.stream.synchronize()
+            d2h.synchronize()
+            st3.sync()
+            e2e_s = max_over_ranks(time.perf_counter() - t0)
+        checksum = float(out_host[: N * N].double().abs().sum())
+        st3.close()
+        e2e = {"value": world * pts_rank * Ke / e2e_s, "unit": UNIT, "h2d_bytes_per_step": pts_rank * 16,
+               "d2h_bytes_per_step": pts_rank * 28, "steps": Ke, "ms_per_step": 1e3 * e2e_s / Ke,
+               "api": "per rank and step: h0/h0conj from pinned host memory (H2D) -> mw_tiles_set_h0 -> mw_tiles_generate_allgather "
+                      "-> mw_tiles_wait -> this rank's slot of the GATHERED buffer to pinned host memory (D2H); the all-gather is "
+                      "inside the timed region", "height_abs_sum_tile0": checksum}
+
+    # ---- the other BASELINE configs + CPU baseline (rank 0, N = 1 only) ----
+    extras = None
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        from oracle import cref
-        cref.build()
-        verts = args.cpu_vertices
-        rate, dt = cpu_reference_rate(N, 1000, verts, 1)
-        cpu = {"value": rate, "unit": UNIT, "cores": 1, "kind": "port",
-               "sample": f"{verts} of {N * N} vertices of the same {N}x{N} grid through the literal "
-                         f"FFTMesh.Displacement loop (oracle/ref_fftmesh.c), 1 thread as Unity runs it; {dt:.1f} s",
-               "host_threads_available": len(os.sched_getaffinity(0))}
-        try:
-            frate, fdt = cpu_fft_form_rate(N, 1000)
-            cpu["fft_form"] = {"value": frate, "unit": UNIT, "cores": 1, "kind": "port, transform form -- NOT what the reference "
-                               "does (it evaluates the O(N^4) direct sum above)",
-                               "sample": f"one full {N}x{N} frame: numpy fp64 ifft2 x 5 + extraction (oracle/ref_fft64.py), {fdt:.2f} s"}
-        except Exception as e:  # noqa: BLE001
-            cpu["fft_form"] = {"error": repr(e)}
+    if rank == 0 and world == 1:
+        if not args.no_extra_configs:
+            try:
+                extras = extra_configs(mw, torch, stream, peak)
+            except Exception as e:  # noqa: BLE001
+                extras = {"error": repr(e)}
+        if not args.no_cpu_baseline:
+            from oracle import cref
+            cref.build()
+            verts = args.cpu_vertices
+            rate, dt = cpu_reference_rate(N, 1000, verts, 1)
+            cpu = {"value": rate, "unit": UNIT, "cores": 1, "kind": "port",
+                   "sample": f"{verts} of {N * N} vertices of the same {N}x{N} grid through the literal "
+                             f"FFTMesh.Displacement loop (oracle/ref_fftmesh.c), 1 thread as Unity runs it; {dt:.1f} s",
+                   "host_threads_available": len(os.sched_getaffinity(0))}
+            try:
+                frate, fdt = cpu_fft_form_rate(N, 1000)
+                cpu["fft_form"] = {"value": frate, "unit": UNIT, "cores": 1, "kind": "port, transform form -- NOT what the reference "
+                                   "does (it evaluates the O(N^4) direct sum above)",
+                                   "sample": f"one full {N}x{N} frame: numpy fp64 ifft2 x 5 + extraction (oracle/ref_fft64.py), {fdt:.2f} s"}
+            except Exception as e:  # noqa: BLE001
+                cpu["fft_form"] = {"error": repr(e)}
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic (device Philox4x32-10 + Phillips spectrum, seed 1000+tile)",
-            "config": workload_config(args, world, st.gather_impl), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+            "config": workload_config(args, world, main["impl"]), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roof, "cpu_baseline": cpu,
-            "achieved_hbm_gbs_pipeline": round(ALG_BYTES_PIPELINE * pts_rank * K / (compute_ms * 1e-3) / 1e9, 1),
         }
+        if extras is not None:
+            line["configs"] = extras
         if world > 1:
-            slot = st.layout.slot_bytes
+            def arm(r):
+                g = r["gather_ms"] / K
+                return {"impl": r["impl"], "value": world * pts_rank * K / (r["ms"] * 1e-3), "ms_per_step": r["ms"] / K,
+                        "compute_ms_per_step": r["compute_ms"] / K, "allgather_ms_per_step": g,
+                        "allgather_busbw_gbs": round(slot_bytes * (world - 1) / (g * 1e-3) / 1e9, 1) if g else None}
+            floor_nom = slot_bytes * (world - 1) / (NVLINK_NOMINAL_GBS * 1e9) * 1e3
+            floor_meas = slot_bytes * (world - 1) / (NVLINK_PEER_COPY_GBS * 1e9) * 1e3
             line["multi_gpu"] = {
-                "compute_only_value": world * pts_rank * K / (compute_ms * 1e-3), "compute_ms_per_step": compute_ms / K,
-                "allgather_ms_per_step": gather_ms / K, "allgather_bytes_per_rank": slot,
-                "allgather_busbw_gbs": round(slot * (world - 1) / (gather_ms / K * 1e-3) / 1e9, 1) if gather_ms else None,
-                "nvlink_peer_copy_peak_gbs": 770.0, "gather_impl": st.gather_impl, "p2p_error": st.p2p_error,
+                "compute_only_value": world * pts_rank * K / (compute_ms * 1e-3),
+                "allgather_bytes_per_rank": slot_bytes, "ingress_bytes_per_rank_per_step": slot_bytes * (world - 1),
+                "ingress_floor_ms": round(floor_nom, 4), "ingress_floor_ms_at_measured_peer_copy": round(floor_meas, 4),
+                "ingress_floor_note": f"every rank must RECEIVE (world - 1) x {slot_bytes / 1e6:.1f} MB per step through its NVLink "
+                                      f"ingress: {NVLINK_NOMINAL_GBS:.0f} GB/s nominal, {NVLINK_PEER_COPY_GBS:.0f} GB/s measured peer copy",
+                "value_ceiling_at_floor": world * pts_rank / (max(floor_nom, compute_ms / K) * 1e-3),
+                "arms": {"peer": arm(main), "nccl": arm(nccl)},
+                "default_arm": "peer", "rank0_numa_binding": numa,
             }
         emit(line)
-    st.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -426,12 +611,13 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
-    ap.add_argument("--resolution", type=int, default=1024)
-    ap.add_argument("--tiles", type=int, default=16)
+    ap.add_argument("--resolution", type=int, default=None, help="default: 1024 at N = 1 (configs[2]), 2048 at N > 1 (configs[4])")
+    ap.add_argument("--tiles", type=int, default=None, help="tiles per GPU; default: 16 at N = 1, 1 at N > 1")
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--cpu-vertices", type=int, default=128, help="vertices in the single-thread CPU baseline sample")
     ap.add_argument("--ref-step-seconds", type=float, default=1.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra-configs", action="store_true", help="skip the other BASELINE configs (64^2, 256^2, Gerstner, ...)")
     args = ap.parse_args()
     with _CleanStdout() as out:
         _OUT = out

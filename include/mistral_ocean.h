@@ -292,20 +292,92 @@ int mw_wave_displace(const mw_wave_params* p, const float* pos_xyz, float* out_x
                      void* cuda_stream);
 
 /*
- * Multi-GPU tile sets: peer-memory plumbing for the one collective of the path, the all-gather of the
- * final float buffers.  No reference counterpart (Scripts/FFTMesh.cs runs one mesh on one device; tiles never exchange data
- * while being generated).  One process per GPU: every rank exports the buffer its peers write its gathered slots into,
- * opens the peers' buffers from its own device, and pushes its slot with one asynchronous copy per peer -- copy engines over
- * NVLink, no SMs.  Fencing between ranks is the host's business (mistral-water_b200/tiles.py uses two 4-byte NCCL all-reduces).
- *   mw_peer_export : CUDA IPC handle of the allocation `dev_ptr` lives in + the pointer's offset inside it
- *   mw_peer_open   : map an exported allocation for direct access from `device` (once per allocation per process)
- *   mw_peer_copy   : asynchronous device-to-device copy on `cuda_stream` (either side may be a peer mapping)
+ * ---------------------------------------------------------------------------------------------
+ * Multi-GPU tile sets (BASELINE config 5): independent ocean tiles, one rank per GPU, and the ONE
+ * collective of the path -- the in-place all-gather of the final float buffers [height | hds | normal | whitecap] (28 B per
+ * grid point), after which every rank holds every tile.  No reference counterpart: Scripts/FFTMesh.cs runs one mesh on one
+ * device, and nothing in EvaluateWaves (:224-280) couples two meshes, which is why tiles shard with no other exchange.
+ *
+ * Rank r generates tiles [r * tiles_per_rank, (r + 1) * tiles_per_rank): tile k uses seed `ocean.seed + k` and the wind
+ * (ocean.wind_x, ocean.wind_y) rotated by `wind_step_deg * (r * tiles_per_rank)` degrees (all tiles of a rank share its wind).
+ * The engine writes straight into the rank's slot of the gather buffer; the handle owns the buffers, the streams, the
+ * peer mappings and the NCCL communicators.
+ *
+ * Two process models, one API:
+ *   single process (rank == -1)   the reference's host model (one Unity process): the handle drives all `world` devices --
+ *                                 ncclCommInitAll + grouped ncclAllGather, or peer copies fenced by CUDA events;
+ *   one process per GPU (rank>=0) each process creates its rank, then the ranks swap fixed-size blobs (CUDA IPC handles of
+ *                                 the gather buffers and flag words; rank 0's blob carries the ncclUniqueId) by whatever
+ *                                 means the host has -- mw_tiles_export / mw_tiles_connect.
+ * Two ways to carry out the all-gather (`gather`):
+ *   MW_GATHER_NCCL  one in-place ncclAllGather per frame (libnccl.so.2 is loaded at run time; absent => MW_E_NCCL);
+ *   MW_GATHER_PEER  every rank pushes its slot into the peers' buffers over NVLink with the copy engines -- no SM is taken
+ *                   from the frame kernels.  Ranks in different processes are fenced by stream memory operations on flag
+ *                   words in peer memory (cuStreamWriteValue32 / cuStreamWaitValue32): no kernel, no host round trip.
+ * Frames are double-buffered: the gather of frame k (communication streams) runs under the generation of frame k + 1.
+ * Contract for the returned buffers: the buffer of frame k is rewritten by frame k + 2; all reads of it must have been
+ * enqueued on the user stream (mw_tiles_set_stream; default: the handle's own) before the call that generates frame k + 2.
  */
-#define MW_PEER_HANDLE_BYTES 64
-int mw_peer_export(const void* dev_ptr, void* handle64, uint64_t* offset);
-int mw_peer_open(int device, const void* handle64, void** base);
-int mw_peer_close(int device, void* base);
-int mw_peer_copy(void* dst, const void* src, uint64_t bytes, void* cuda_stream);
+#define MW_TILES_MAX_WORLD 16
+#define MW_TILES_BLOB_BYTES 512
+enum { MW_GATHER_NCCL = 0, MW_GATHER_PEER = 1 };
+enum { MW_TILES_ASYNC = 1u << 0 /* generate_allgather only enqueues; mw_tiles_wait / mw_tiles_sync order the results */ };
+
+typedef struct mw_tiles_params {
+    mw_ocean_params ocean;   /* per-tile parameters; .tiles and .device are ignored (tiles_per_rank / devices[] below),
+                                .flags may carry MW_PROFILE                                                              */
+    int32_t world;           /* number of ranks = GPUs, 1..MW_TILES_MAX_WORLD                                           */
+    int32_t rank;            /* -1: this process drives all ranks; r >= 0: this process is rank r                       */
+    int32_t tiles_per_rank;
+    int32_t gather;          /* MW_GATHER_NCCL | MW_GATHER_PEER                                                         */
+    int32_t devices[MW_TILES_MAX_WORLD]; /* CUDA ordinal of rank r (rank >= 0: only devices[rank] is read)              */
+    float wind_step_deg;     /* config 5: 45                                                                            */
+    uint32_t flags;          /* MW_TILES_ASYNC                                                                          */
+} mw_tiles_params;
+
+typedef struct mw_tiles_layout {
+    int64_t slot_floats;     /* floats per rank slot = tiles_per_rank * N * N * 7                                       */
+    int64_t height_off, disp_off, normal_off, whitecap_off; /* float offsets of the planar fields inside a slot:
+                                field f of local tile l, grid index idx, component c sits at
+                                f_off + (l * N * N + idx) * comps(f) + c                                                */
+    int32_t world, tiles_per_rank, resolution, local_ranks; /* local_ranks: `world` (single process) or 1              */
+} mw_tiles_layout;
+
+typedef struct mw_tiles mw_tiles; /* opaque */
+
+int mw_tiles_create(const mw_tiles_params* params, mw_tiles** out);
+void mw_tiles_destroy(mw_tiles* t);
+int mw_tiles_get_layout(const mw_tiles* t, mw_tiles_layout* layout);
+/* One process per GPU only: this rank's blob (MW_TILES_BLOB_BYTES), then all `world` blobs in rank order.  connect() is
+ * collective (every rank must call it; it opens the peer mappings, runs a flag handshake, or ncclCommInitRank). */
+int mw_tiles_export(mw_tiles* t, void* blob);
+int mw_tiles_connect(mw_tiles* t, const void* blobs);
+/* Device-side h0 init of every local tile (mw_ocean_init_spectrum). */
+int mw_tiles_init_spectrum(mw_tiles* t);
+/* mw_ocean_set_h0 for local rank i: DEVICE pointers on that rank's device, [tiles_per_rank][N*N] Vector2 each, read in
+ * user-stream order (an upload enqueued on the user stream before this call is complete when the engine reads it). */
+int mw_tiles_set_h0(mw_tiles* t, int local_rank, const float* h0, const float* h0conj);
+/* The user stream(s) the calls below are ordered against: `streams[i]` for local rank i (cudaStream_t; NULL entries or a
+ * NULL array select the handle's own). */
+int mw_tiles_set_stream(mw_tiles* t, void* const* streams);
+/*
+ * One frame: EvaluateWaves(t) of every local tile into its rank's slot, then the all-gather.  gathered[i] receives local
+ * rank i's gather buffer of this frame, [world][slot_floats] floats on that rank's device (may be NULL).  Without
+ * MW_TILES_ASYNC the call returns when the buffers are complete; with it, see mw_tiles_wait.
+ */
+int mw_tiles_generate_allgather(mw_tiles* t, float time, void** gathered);
+/* The two halves, for hosts (and benches) that want them apart: compute only / gather of the frame last generated. */
+int mw_tiles_generate_local(mw_tiles* t, float time, void** gathered);
+int mw_tiles_allgather(mw_tiles* t);
+/* The user stream(s) wait (on the device, not the host) for the gather of the latest frame (frames_back = 0) or of the
+ * one before (1).  mw_tiles_sync blocks the host until everything queued has completed and reports NCCL's asynchronous
+ * errors (ncclCommGetAsyncError) as MW_E_NCCL. */
+int mw_tiles_wait(mw_tiles* t, int frames_back);
+int mw_tiles_sync(mw_tiles* t);
+/* Which implementation runs the gather (MW_GATHER_*), and the text of why a requested one was not available. */
+int mw_tiles_gather_impl(const mw_tiles* t);
+/* The mw_ocean handle of local rank i (borrowed: owned by the tile set), e.g. for mw_ocean_set_h0 / mw_ocean_kernel_times. */
+mw_ocean* mw_tiles_ocean(mw_tiles* t, int local_rank);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

@@ -13,7 +13,7 @@ LIBDIR = os.path.join(HERE, "lib")
 # developer hook: MW_LIB_SUFFIX=_x MW_NVCC_DEFS="-DFOO=1" builds an experiment variant next to the product library
 SUFFIX = os.environ.get("MW_LIB_SUFFIX", "")
 LIB = os.path.join(LIBDIR, f"libmistral_ocean{SUFFIX}.so")
-SOURCES = ["mw_ocean.cu", "mw_fft2d.cu", "mw_gerstner.cu", "mw_renderer.cu", "mw_peer.cu"]
+SOURCES = ["mw_ocean.cu", "mw_fft2d.cu", "mw_gerstner.cu", "mw_renderer.cu", "mw_tiles.cu"]
 HEADERS = ["mw_common.cuh", "mw_fft.cuh", "mw_ocean_kernels.cuh", "mw_renderer_kernels.cuh", "mw_layout.cuh", os.path.join("..", "..", "include", "mistral_ocean.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -60,7 +60,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         list(ex.map(run, jobs))
     objs = [os.path.join(objdir, s.replace(".cu", ".o")) for s in SOURCES]
     if force or jobs or _stale(LIB, objs):
-        run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs)
+        run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + ["-ldl"])
     return LIB
 
 

@@ -509,13 +509,13 @@ static int run_frame_n(mw_ocean* o, mwk::RowArgs ra, mwk::ColArgs ca)
 #define MW_ROWS_RP_256 4
 #endif
 #ifndef MW_ROWS_MINB_256
-#define MW_ROWS_MINB_256 2
+#define MW_ROWS_MINB_256 3
 #endif
 #ifndef MW_ROWS_MINB_512
-#define MW_ROWS_MINB_512 2
+#define MW_ROWS_MINB_512 3
 #endif
 #ifndef MW_ROWS_MINB_2048
-#define MW_ROWS_MINB_2048 1
+#define MW_ROWS_MINB_2048 2
 #endif
 static int run_frame(mw_ocean* o, const mwk::RowArgs& ra, const mwk::ColArgs& ca)
 {

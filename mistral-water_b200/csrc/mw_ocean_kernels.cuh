@@ -518,11 +518,13 @@ __host__ __device__ constexpr int nstage_slots(int N) { return N >= 256 ? MW_NST
 // Register cap per resolution = what decides the CTAs per SM of this kernel ((W + 1) N / 16 threads per CTA):
 // N = 1024: 576 threads, one CTA per SM either way; N = 512: 288 threads, 112 registers let two CTAs share an SM
 // (128 leaves one); N = 256: 144 threads, 96 registers -> four CTAs (the shared-memory limit) instead of three.
+// (measured, profiles/r02_occ_sweep.jsonl: 112 / 96 registers here + 3 / 3 / 2 pass-1 CTAs per SM at N = 256 / 512 / 2048
+//  take 7-8 % off the frame at those resolutions: 256^2 x 256 301 -> 278 us, 512^2 x 64 431 -> 403 us, one 2048^2 tile 154 -> 142 us)
 #ifndef MW_COLS_MAXREG_512
-#define MW_COLS_MAXREG_512 128
+#define MW_COLS_MAXREG_512 112
 #endif
 #ifndef MW_COLS_MAXREG_256
-#define MW_COLS_MAXREG_256 128
+#define MW_COLS_MAXREG_256 96
 #endif
 __host__ __device__ constexpr int cols_maxreg(int N)
 {

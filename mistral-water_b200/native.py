@@ -33,9 +33,14 @@ EXPORTS = (
     "mw_gerstner_displace", "mw_renderer_create", "mw_renderer_destroy", "mw_renderer_render_initial",
     "mw_renderer_set_initial", "mw_renderer_get_initial", "mw_renderer_set_phase", "mw_renderer_get_phase",
     "mw_renderer_set_params", "mw_renderer_generate_texture", "mw_renderer_sync", "mw_mesh_generate", "mw_wave_displace",
-    "mw_peer_export", "mw_peer_open", "mw_peer_close", "mw_peer_copy",
+    "mw_tiles_create", "mw_tiles_destroy", "mw_tiles_get_layout", "mw_tiles_export", "mw_tiles_connect",
+    "mw_tiles_init_spectrum", "mw_tiles_set_h0", "mw_tiles_set_stream", "mw_tiles_generate_allgather", "mw_tiles_generate_local",
+    "mw_tiles_allgather", "mw_tiles_wait", "mw_tiles_sync", "mw_tiles_gather_impl", "mw_tiles_ocean",
 )
-MW_PEER_HANDLE_BYTES = 64
+MW_TILES_MAX_WORLD = 16
+MW_TILES_BLOB_BYTES = 512
+MW_GATHER_NCCL, MW_GATHER_PEER = 0, 1
+MW_TILES_ASYNC = 1 << 0
 
 
 class MwError(RuntimeError):
@@ -52,6 +57,17 @@ class OceanParams(C.Structure):
         ("seed", C.c_uint64), ("device", C.c_int32), ("tiles", C.c_int32), ("flags", C.c_uint32),
         ("reserved", C.c_uint32),
     ]
+
+
+class TilesParams(C.Structure):
+    _fields_ = [("ocean", OceanParams), ("world", C.c_int32), ("rank", C.c_int32), ("tiles_per_rank", C.c_int32),
+                ("gather", C.c_int32), ("devices", C.c_int32 * 16), ("wind_step_deg", C.c_float), ("flags", C.c_uint32)]
+
+
+class TilesLayout(C.Structure):
+    _fields_ = [("slot_floats", C.c_int64), ("height_off", C.c_int64), ("disp_off", C.c_int64), ("normal_off", C.c_int64),
+                ("whitecap_off", C.c_int64), ("world", C.c_int32), ("tiles_per_rank", C.c_int32), ("resolution", C.c_int32),
+                ("local_ranks", C.c_int32)]
 
 
 class OceanOut(C.Structure):
@@ -137,6 +153,23 @@ def load() -> C.CDLL:
     lib.mw_renderer_sync.argtypes = [vp]
     lib.mw_mesh_generate.argtypes = [C.c_int, C.c_int32, C.c_float, fp, fp, fp, fp]
     lib.mw_wave_displace.argtypes = [C.POINTER(WaveParams), fp, fp, fp, C.c_int64, C.c_float, vp]
+    lib.mw_tiles_create.argtypes = [C.POINTER(TilesParams), C.POINTER(vp)]
+    lib.mw_tiles_destroy.argtypes = [vp]
+    lib.mw_tiles_destroy.restype = None
+    lib.mw_tiles_get_layout.argtypes = [vp, C.POINTER(TilesLayout)]
+    lib.mw_tiles_export.argtypes = [vp, vp]
+    lib.mw_tiles_connect.argtypes = [vp, vp]
+    lib.mw_tiles_init_spectrum.argtypes = [vp]
+    lib.mw_tiles_set_h0.argtypes = [vp, C.c_int, fp, fp]
+    lib.mw_tiles_set_stream.argtypes = [vp, C.POINTER(vp)]
+    lib.mw_tiles_generate_allgather.argtypes = [vp, C.c_float, C.POINTER(vp)]
+    lib.mw_tiles_generate_local.argtypes = [vp, C.c_float, C.POINTER(vp)]
+    lib.mw_tiles_allgather.argtypes = [vp]
+    lib.mw_tiles_wait.argtypes = [vp, C.c_int]
+    lib.mw_tiles_sync.argtypes = [vp]
+    lib.mw_tiles_gather_impl.argtypes = [vp]
+    lib.mw_tiles_ocean.argtypes = [vp, C.c_int]
+    lib.mw_tiles_ocean.restype = vp
     _lib = lib
     return lib
 
@@ -144,28 +177,6 @@ def load() -> C.CDLL:
 def check(rc: int) -> None:
     if rc != MW_OK:
         raise MwError(rc, load().mw_last_error().decode("utf-8", "replace"))
-
-
-def peer_export(dev_ptr: int) -> tuple[bytes, int]:
-    """(CUDA IPC handle of the allocation dev_ptr lives in, offset of dev_ptr inside it)."""
-    h = C.create_string_buffer(MW_PEER_HANDLE_BYTES)
-    off = C.c_uint64(0)
-    check(load().mw_peer_export(C.c_void_p(dev_ptr), h, C.byref(off)))
-    return h.raw, int(off.value)
-
-
-def peer_open(device: int, handle: bytes) -> int:
-    base = C.c_void_p()
-    check(load().mw_peer_open(int(device), C.c_char_p(handle), C.byref(base)))
-    return int(base.value)
-
-
-def peer_close(device: int, base: int) -> None:
-    check(load().mw_peer_close(int(device), C.c_void_p(base)))
-
-
-def peer_copy(dst: int, src: int, nbytes: int, stream: int) -> None:
-    check(load().mw_peer_copy(C.c_void_p(dst), C.c_void_p(src), C.c_uint64(nbytes), C.c_void_p(stream)))
 
 
 def launch_count() -> int:

@@ -1,13 +1,15 @@
 """Independent ocean tiles sharded one-per-GPU, with ONE all-gather of the final float buffers
 (BASELINE config 5).
 
-One process per GPU (torchrun); rank r owns tiles [r * tpr, (r + 1) * tpr).  Tiles never exchange
-data while being generated (nothing in FFTMesh.cs couples two meshes), so the only collective is
-the final in-place all-gather: every rank's engine writes its outputs straight into its own slot of
-the gather buffer (device pointers handed to mw_ocean_generate), then
-`all_gather_into_tensor(gather, gather[rank])` runs over NCCL / NVLink.
+Rank r owns tiles [r * tpr, (r + 1) * tpr).  Tiles never exchange data while being generated (nothing
+in FFTMesh.cs couples two meshes), so the only collective is the final in-place all-gather.  The whole
+mechanism -- gather buffers, streams, double buffering, fences, NCCL communicators, peer mappings --
+lives behind the C ABI (mw_tiles_*, csrc/mw_tiles.cu); this module is the ctypes caller:
 
-torch is used for what it is good at here -- device memory, streams, the process group.
+  TileSet       one mw_tiles handle: all GPUs from ONE process (rank=None; the reference's host model,
+                one Unity process) or one process per GPU (rank=r; blobs swapped by `exchange`)
+  ShardedTiles  the torchrun-shaped convenience around it (blobs travel through torch.distributed);
+                with `make_generator` it runs a CPU stub instead (gloo tests of layout / sharding)
 """
 from __future__ import annotations
 
@@ -56,218 +58,200 @@ class TileLayout:
 
 def tile_wind(base_wind, global_tile: int, step_deg: float = 45.0):
     """Config 5: tile k's wind is the base wind rotated by 45 deg * k."""
-    a = math.radians(step_deg * global_tile)
+    a = (step_deg * global_tile) * math.pi / 180.0   # same operation order as csrc/mw_tiles.cu (rotate_wind)
     c, s = math.cos(a), math.sin(a)
     return (c * base_wind[0] - s * base_wind[1], s * base_wind[0] + c * base_wind[1])
 
 
-class ShardedTiles:
-    """This rank's share of the tile set + the gather buffer.
+class _DevArray:
+    """A device allocation owned by the library, presented through __cuda_array_interface__ (zero-copy torch view)."""
 
-    `make_generator(rank_params) -> callable(t, slot_views: dict[str, Tensor])` builds the local
-    producer; the default is the CUDA engine (mistral_water_b200.Ocean with device pointers).  The
-    CPU `gloo` tests inject a stub there to exercise the sharding / layout / collective logic.
+    def __init__(self, ptr: int, nfloats: int):
+        self.__cuda_array_interface__ = {"shape": (int(nfloats),), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
+
+
+class TileSet:
+    """One mw_tiles handle (include/mistral_ocean.h, "Multi-GPU tile sets").  Every method is one C-ABI call.
+
+    rank=None : this process drives all `world` GPUs (`devices`, default 0..world-1); no blob exchange, no
+                torch.distributed -- what a single C# host process does.
+    rank=r    : one process per GPU; `exchange(blob) -> [blob of rank 0, blob of rank 1, ...]` is any all-gather of
+                512-byte strings the host has (ShardedTiles passes torch.distributed.all_gather_object).
+    """
+
+    def __init__(self, N: int, world: int, rank: int | None = None, devices=None, tiles_per_rank: int = 1,
+                 gather: str = "peer", base_seed: int = 1000, wind=(5.0, 3.0), amplitude: float = 0.01,
+                 unit_width: float = 1.0, choppiness: float = 1.0, wind_step_deg: float = 45.0, asynchronous: bool = True,
+                 profile: bool = False, exchange=None):
+        import ctypes as C
+
+        import numpy as np
+
+        from . import native
+
+        self._C, self._native = C, native
+        self._lib = native.load()
+        self.N, self.world, self.rank, self.tiles_per_rank = int(N), int(world), rank, int(tiles_per_rank)
+        devices = list(range(world)) if devices is None else list(devices)
+        p = native.TilesParams()
+        length = float(np.float32(N) * np.float32(unit_width))
+        p.ocean = native.OceanParams(int(N), float(unit_width), length, float(choppiness), float(amplitude), float(wind[0]),
+                                     float(wind[1]), 1.0, int(base_seed), 0, 1, native.MW_PROFILE if profile else 0, 0)
+        p.world, p.rank, p.tiles_per_rank = self.world, (-1 if rank is None else int(rank)), self.tiles_per_rank
+        p.gather = {"nccl": native.MW_GATHER_NCCL, "peer": native.MW_GATHER_PEER, "p2p": native.MW_GATHER_PEER}[gather]
+        for i, d in enumerate(devices[:native.MW_TILES_MAX_WORLD]):
+            p.devices[i] = int(d)
+        p.wind_step_deg = float(wind_step_deg)
+        p.flags = native.MW_TILES_ASYNC if asynchronous else 0
+        self.devices = devices
+        self._h = C.c_void_p()
+        native.check(self._lib.mw_tiles_create(C.byref(p), C.byref(self._h)))
+        lay = native.TilesLayout()
+        native.check(self._lib.mw_tiles_get_layout(self._h, C.byref(lay)))
+        self.slot_floats, self.local_ranks = int(lay.slot_floats), int(lay.local_ranks)
+        self.field_off = {"height": int(lay.height_off), "disp": int(lay.disp_off), "normal": int(lay.normal_off),
+                          "whitecap": int(lay.whitecap_off)}
+        if rank is not None and world > 1:
+            if exchange is None:
+                raise ValueError("one process per GPU needs `exchange` to swap the ranks' blobs")
+            blob = C.create_string_buffer(native.MW_TILES_BLOB_BYTES)
+            native.check(self._lib.mw_tiles_export(self._h, blob))
+            blobs = exchange(blob.raw)
+            if len(blobs) != world or any(len(b) != native.MW_TILES_BLOB_BYTES for b in blobs):
+                raise ValueError("exchange() must return one 512-byte blob per rank, in rank order")
+            allb = C.create_string_buffer(b"".join(blobs), native.MW_TILES_BLOB_BYTES * world)
+            native.check(self._lib.mw_tiles_connect(self._h, allb))
+        self.gather_impl = {native.MW_GATHER_NCCL: "nccl", native.MW_GATHER_PEER: "peer"}[int(self._lib.mw_tiles_gather_impl(self._h))]
+
+    # -- lifetime
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self._lib.mw_tiles_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- calls
+    def _ptrs(self):
+        return (self._C.c_void_p * self.local_ranks)()
+
+    def init_spectrum(self) -> None:
+        self._native.check(self._lib.mw_tiles_init_spectrum(self._h))
+
+    def set_h0(self, local_rank: int, h0_ptr: int, h0conj_ptr: int) -> None:
+        """Device pointers on that rank's device; read in user-stream order."""
+        self._native.check(self._lib.mw_tiles_set_h0(self._h, int(local_rank), self._C.c_void_p(h0_ptr), self._C.c_void_p(h0conj_ptr)))
+
+    def set_stream(self, streams) -> None:
+        """streams: one cudaStream_t (int) per local rank, or None for the handle's own."""
+        arr = None
+        if streams is not None:
+            arr = self._ptrs()
+            for i, s in enumerate(streams):
+                arr[i] = int(s) if s else None
+        self._native.check(self._lib.mw_tiles_set_stream(self._h, arr))
+
+    def generate_allgather(self, t: float) -> list[int]:
+        out = self._ptrs()
+        self._native.check(self._lib.mw_tiles_generate_allgather(self._h, float(t), out))
+        return [int(x) for x in out]
+
+    def generate_local(self, t: float) -> list[int]:
+        out = self._ptrs()
+        self._native.check(self._lib.mw_tiles_generate_local(self._h, float(t), out))
+        return [int(x) for x in out]
+
+    def allgather(self) -> None:
+        self._native.check(self._lib.mw_tiles_allgather(self._h))
+
+    def wait(self, frames_back: int = 0) -> None:
+        self._native.check(self._lib.mw_tiles_wait(self._h, int(frames_back)))
+
+    def sync(self) -> None:
+        self._native.check(self._lib.mw_tiles_sync(self._h))
+
+    def ocean_handle(self, local_rank: int = 0) -> int:
+        return int(self._lib.mw_tiles_ocean(self._h, int(local_rank)) or 0)
+
+    def as_tensor(self, ptr: int, local_rank: int = 0):
+        """[world][slot_floats] torch view of a gather buffer returned by generate_*."""
+        import torch
+
+        dev = self.devices[local_rank if self.rank is None else self.rank]
+        return torch.as_tensor(_DevArray(ptr, self.world * self.slot_floats), device=torch.device("cuda", dev)).view(self.world, self.slot_floats)
+
+
+class ShardedTiles:
+    """This rank's share of the tile set under torchrun (one process per GPU).
+
+    CUDA: a TileSet whose blobs travel through torch.distributed; `stream` (a torch stream) is the user stream the
+    calls are ordered against.  `make_generator(rank_params) -> callable(t, slot_views)` replaces the engine by a
+    stub for the CPU `gloo` tests of the sharding / layout / collective logic.
     """
 
     def __init__(self, N: int, rank: int, world: int, tiles_per_rank: int = 1, base_seed: int = 1000,
                  wind=(5.0, 3.0), amplitude: float = 0.01, unit_width: float = 1.0, choppiness: float = 1.0,
-                 device=None, group=None, make_generator=None):
+                 device=None, group=None, make_generator=None, gather: str | None = None, profile: bool = False):
         import torch
 
         self.torch = torch
         self.layout = TileLayout(N, world, tiles_per_rank)
         self.rank, self.world, self.group = rank, world, group
         self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
-        # two gather buffers: the all-gather of frame k (communication stream) overlaps the generation of
-        # frame k + 1 (engine stream) -- see generate_pipelined()
-        self.nbuf = 2 if world > 1 else 1
-        self.gathers = [torch.empty((world, self.layout.slot_floats), dtype=torch.float32, device=self.device)
-                        for _ in range(self.nbuf)]
-        self.gather = self.gathers[0]
-        self._frame = 0
-        self._cur_buf = 0
-        # how the one collective is carried out: "p2p" = every rank pushes its slot straight into the peers' gather
-        # buffers over NVLink with the copy engines (CUDA IPC peer memory, no SMs taken from the frame kernels) and a
-        # 4-byte NCCL all-reduce closes the step; "nccl" = ncclAllGather.  MW_GATHER=nccl|p2p overrides.
-        self.gather_impl, self.p2p_error = "nccl", None
-        if world > 1 and self.device.type == "cuda" and make_generator is None:
-            import os
-            want = os.environ.get("MW_GATHER", "p2p")
-            if want == "p2p":
-                self._setup_p2p()
         self.rank_params = dict(resolution=N, unit_width=unit_width, choppiness=choppiness, amplitude=amplitude,
                                 wind=tile_wind(wind, self.layout.global_tile(rank, 0)),
                                 seed=base_seed + self.layout.global_tile(rank, 0), tiles=tiles_per_rank)
-        self._gen = (make_generator or self._cuda_generator)(self.rank_params)
+        self.tileset = None
+        if make_generator is not None or self.device.type != "cuda":
+            # CPU stub path: one gather buffer, the collective through the process group (gloo)
+            if make_generator is None:
+                raise RuntimeError("ShardedTiles on a CPU device needs make_generator: the engine has no CPU path")
+            self.gather_impl = "nccl"
+            self.gather = torch.empty((world, self.layout.slot_floats), dtype=torch.float32, device=self.device)
+            self._gen = make_generator(self.rank_params)
+            return
+        import os
 
-    def _cuda_generator(self, rp):
-        from .ocean import Ocean
+        import torch.distributed as dist
 
-        torch = self.torch
+        def exchange(blob: bytes):
+            out = [None] * world
+            dist.all_gather_object(out, blob, group=group)
+            return out
+
         dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        devices = [0] * world
+        devices[rank] = dev_index
+        self.tileset = TileSet(N, world, rank=rank, devices=devices, tiles_per_rank=tiles_per_rank,
+                               gather=gather or os.environ.get("MW_GATHER", "peer"), base_seed=base_seed, wind=wind,
+                               amplitude=amplitude, unit_width=unit_width, choppiness=choppiness, asynchronous=True,
+                               profile=profile, exchange=exchange if world > 1 else None)
+        self.gather_impl = self.tileset.gather_impl
         self.stream = torch.cuda.Stream(device=self.device)
-        self.ocean = Ocean(device=dev_index, device_ptrs=True, **rp)
-        self.ocean.set_stream(self.stream.cuda_stream)
-        self.ocean.init_spectrum()
-        self.ocean.sync()
+        self.tileset.set_stream([self.stream.cuda_stream])
+        self.tileset.init_spectrum()
+        self.tileset.sync()
+        self.gather = None
 
-        def run(t, views):
-            self.ocean.generate(t, views)
-
-        return run
-
-    # ------------------------------------------------------------------ peer-memory all-gather
-    def _setup_p2p(self) -> None:
-        """Open every peer's gather buffers from THIS rank's device through the library's CUDA IPC entry points
-        (mw_peer_export / mw_peer_open: one process per GPU, all GPUs of the node visible, NVLink peer access).
-        Any failure leaves gather_impl == "nccl" with the reason in p2p_error; the ranks agree on the outcome."""
-        torch = self.torch
-        import torch.distributed as dist
-        from . import native
-
-        ok, err = True, None
-        self._peer_ptr, self._peer_bases = {}, []
-        try:
-            mine = [native.peer_export(g.data_ptr()) for g in self.gathers]   # (64-byte IPC handle, offset) per buffer
-            allh = [None] * self.world
-            dist.all_gather_object(allh, (self.device.index, mine), group=self.group)
-            opened = {}
-            for r, (dev_index, handles) in enumerate(allh):
-                if r == self.rank:
-                    continue
-                if not torch.cuda.can_device_access_peer(self.device.index, dev_index):
-                    raise RuntimeError(f"no peer access from cuda:{self.device.index} to cuda:{dev_index}")
-                ptrs = []
-                for handle, off in handles:
-                    if handle not in opened:                                  # an allocation is opened once per process
-                        opened[handle] = native.peer_open(self.device.index, handle)
-                        self._peer_bases.append(opened[handle])
-                    ptrs.append(opened[handle] + off)
-                self._peer_ptr[r] = ptrs                                      # rank r's gather buffers, as seen from here
-        except Exception as e:  # noqa: BLE001
-            ok, err = False, repr(e)
-        flag = torch.tensor([1 if ok else 0], device=self.device, dtype=torch.int32)
-        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
-        if int(flag.item()) == 1:
-            self.gather_impl = "p2p"
-            self._push_streams = {r: torch.cuda.Stream(device=self.device) for r in self._peer_ptr}
-            self._push_done = {r: torch.cuda.Event() for r in self._peer_ptr}
-            self._token = torch.zeros(1, device=self.device, dtype=torch.int32)
-        else:
-            self.p2p_error = err or "a peer could not open the buffers"
-            self._close_peers()
-
-    def _close_peers(self) -> None:
-        from . import native
-        for base in getattr(self, "_peer_bases", []):
-            try:
-                native.peer_close(self.device.index, base)
-            except Exception:  # noqa: BLE001
-                pass
-        self._peer_bases, self._peer_ptr = [], {}
-
-    def _push_slots(self, buf: int) -> None:
-        """Enqueue the all-gather of gather buffer `buf` on the current stream (which already waits for this rank's
-        slot to be complete and for this rank's readers of the buffer):
-          1. a 4-byte all-reduce -- every rank has reached this point, so nobody still reads what is about to be overwritten;
-          2. this rank's slot pushed into every peer's buffer (mw_peer_copy), one copy-engine stream per peer, peers
-             visited in a rank-dependent order so that no destination is hit by everybody at once;
-          3. a second 4-byte all-reduce -- when it completes here, every rank's pushes have landed."""
-        torch = self.torch
-        import torch.distributed as dist
-        from . import native
-
-        cur = torch.cuda.current_stream(self.device)
-        dist.all_reduce(self._token, group=self.group)
-        ready = torch.cuda.Event()
-        ready.record(cur)
-        slot_bytes = self.layout.slot_bytes
-        src = self.gathers[buf][self.rank].data_ptr()
-        for i in range(1, self.world):
-            r = (self.rank + i) % self.world
-            ps = self._push_streams[r]
-            ps.wait_event(ready)
-            native.peer_copy(self._peer_ptr[r][buf] + self.rank * slot_bytes, src, slot_bytes, ps.cuda_stream)
-            self._push_done[r].record(ps)
-            cur.wait_event(self._push_done[r])
-        dist.all_reduce(self._token, group=self.group)
-
-    def slot_views(self, rank: int | None = None, buf: int = 0) -> dict:
-        """Field views into one rank's slot (default: ours) of gather buffer `buf`."""
-        slot = self.gathers[buf][self.rank if rank is None else rank]
+    # ------------------------------------------------------------------ views
+    def slot_views(self, rank: int | None = None) -> dict:
+        """Field views into one rank's slot (default: ours) of the current gather buffer."""
+        slot = self.gather[self.rank if rank is None else rank]
         out = {}
         for name, comps in FIELDS:
             b, e = self.layout.field_range(name)
             out[name] = slot[b:e]
         return out
-
-    def generate_local(self, t: float) -> None:
-        """Produce this rank's tiles into its slot (asynchronous on the engine's stream)."""
-        self._gen(float(t), self.slot_views())
-
-    def all_gather(self) -> None:
-        """The one collective: in-place all-gather of the slots."""
-        import torch.distributed as dist
-
-        if self.world == 1:
-            return
-        if self.gather_impl == "p2p":
-            self._push_slots(self._cur_buf)
-            return
-        dist.all_gather_into_tensor(self.gather.view(-1), self.gather[self.rank].view(-1), group=self.group)
-
-    def generate(self, t: float):
-        torch = self.torch
-        self.generate_local(t)
-        if hasattr(self, "stream"):
-            torch.cuda.current_stream(self.device).wait_stream(self.stream)  # NCCL runs after the producer
-        self.all_gather()
-        return self.gather
-
-    def generate_pipelined(self, t: float):
-        """Frame k: generate into gather buffer k % 2 on the engine stream, then all-gather it on a separate
-        communication stream, so that the collective of frame k runs under the generation of frame k + 1.
-        Returns the buffer being gathered; call finish() before reading it."""
-        torch = self.torch
-        if self.world == 1 or not hasattr(self, "stream"):
-            return self.generate(t)
-        if not hasattr(self, "comm_stream"):
-            self.comm_stream = torch.cuda.Stream(device=self.device)
-            self._ev_gen = [torch.cuda.Event() for _ in range(2)]
-            self._ev_comm = [torch.cuda.Event() for _ in range(2)]
-            self._comm_used = [False, False]
-        b = self._frame & 1
-        self._frame += 1
-        self._cur_buf = b
-        ev_user = torch.cuda.Event()
-        ev_user.record(torch.cuda.current_stream(self.device))
-        if self._comm_used[b]:
-            self.stream.wait_event(self._ev_comm[b])      # buffer b is free again once its last gather is done
-        self._gen(float(t), self.slot_views(buf=b))
-        self._ev_gen[b].record(self.stream)
-        import torch.distributed as dist
-        with torch.cuda.stream(self.comm_stream):
-            self.comm_stream.wait_event(self._ev_gen[b])
-            g = self.gathers[b]
-            if self.gather_impl == "p2p":
-                # peers will write into this rank's buffer b: whatever the caller enqueued so far (its reads of the frame
-                # gathered into b two calls ago) comes first
-                self.comm_stream.wait_event(ev_user)
-                self._push_slots(b)
-            else:
-                dist.all_gather_into_tensor(g.view(-1), g[self.rank].view(-1), group=self.group)
-            self._ev_comm[b].record(self.comm_stream)
-        self._comm_used[b] = True
-        self.gather = self.gathers[b]
-        return self.gather
-
-    def finish(self) -> None:
-        """Make the current stream wait for everything generate_pipelined() queued."""
-        torch = self.torch
-        if hasattr(self, "comm_stream"):
-            cur = torch.cuda.current_stream(self.device)
-            cur.wait_stream(self.comm_stream)
-            cur.wait_stream(self.stream)
 
     def tile_view(self, global_tile: int, name: str):
         """Field `name` of any tile, from the gathered buffer: [N*N, comps]."""
@@ -277,9 +261,58 @@ class ShardedTiles:
         n2 = self.layout.N * self.layout.N
         return self.gather[r, b:e].view(self.layout.tiles_per_rank, n2, comps)[l]
 
+    # ------------------------------------------------------------------ frames
+    def _view(self, ptrs):
+        self.gather = self.tileset.as_tensor(ptrs[0])
+        return self.gather
+
+    def generate_local(self, t: float):
+        """Produce this rank's tiles into its slot (asynchronous; no collective)."""
+        if self.tileset is None:
+            self._gen(float(t), self.slot_views())
+            return self.gather
+        return self._view(self.tileset.generate_local(t))
+
+    def all_gather(self) -> None:
+        """The one collective: in-place all-gather of the slots of the frame last generated."""
+        if self.world == 1:
+            return
+        if self.tileset is None:
+            import torch.distributed as dist
+
+            dist.all_gather_into_tensor(self.gather.view(-1), self.gather[self.rank].view(-1).clone(), group=self.group)
+            return
+        self.tileset.allgather()
+
+    def generate(self, t: float):
+        """One frame + its all-gather; the returned buffer is complete once `stream` (the user stream) gets there."""
+        if self.tileset is None:
+            self.generate_local(t)
+            self.all_gather()
+            return self.gather
+        g = self._view(self.tileset.generate_allgather(t))
+        self.tileset.wait(0)
+        return g
+
+    def generate_pipelined(self, t: float):
+        """Frame k: generated into gather buffer k % 2 and gathered on the library's communication streams, so that the
+        collective of frame k runs under the generation of frame k + 1.  Returns the buffer being gathered; call
+        finish() before reading it (on `stream`)."""
+        if self.tileset is None:
+            return self.generate(t)
+        return self._view(self.tileset.generate_allgather(t))
+
+    def finish(self) -> None:
+        """Make the user stream wait for everything generate_pipelined() queued."""
+        if self.tileset is not None:
+            self.tileset.wait(0)
+
+    def sync(self) -> None:
+        if self.tileset is not None:
+            self.tileset.sync()
+
     def close(self) -> None:
-        if getattr(self, "_peer_bases", None):
-            self.torch.cuda.synchronize(self.device)
-            self._close_peers()         # drop the IPC mappings before the owners free their buffers
-        if hasattr(self, "ocean"):
-            self.ocean.close()
+        if self.tileset is not None:
+            self.tileset.sync()
+            self.tileset.close()
+            self.tileset = None

@@ -71,18 +71,32 @@ def test_null_arguments_are_errors_not_crashes(mw):
     assert lib.mw_fft2d(0, 48, 1, -1, x.ctypes.data, x.ctypes.data) == mw.native.MW_E_INVALID_ARG
     assert lib.mw_gerstner_displace(None, None, None, None, 0, 0.0, None) == mw.native.MW_E_INVALID_ARG
     lib.mw_ocean_destroy(None)  # no-op
-    # peer-memory entry points of the multi-GPU tile set
-    import ctypes as C
-    h = C.create_string_buffer(mw.native.MW_PEER_HANDLE_BYTES)
-    off = C.c_uint64(0)
-    base = C.c_void_p()
-    assert lib.mw_peer_export(None, h, C.byref(off)) == mw.native.MW_E_INVALID_ARG
-    assert lib.mw_peer_export(C.c_void_p(4096), None, C.byref(off)) == mw.native.MW_E_INVALID_ARG
-    assert lib.mw_peer_open(0, None, C.byref(base)) == mw.native.MW_E_INVALID_ARG
-    assert lib.mw_peer_open(0, h, None) == mw.native.MW_E_INVALID_ARG
-    assert lib.mw_peer_copy(None, None, C.c_uint64(16), None) == mw.native.MW_E_INVALID_ARG
-    assert lib.mw_peer_close(0, None) == mw.native.MW_OK  # nothing to close
-    assert b"mw_peer" in lib.mw_last_error()
+    # multi-GPU tile sets
+    n = mw.native
+    h = C.c_void_p()
+    assert lib.mw_tiles_create(None, C.byref(h)) == n.MW_E_INVALID_ARG
+    p = n.TilesParams()
+    p.ocean = n.OceanParams(64, 1.0, 64.0, 1.0, 0.01, 5.0, 3.0, 1.0, 1000, 0, 1, 0, 0)
+    p.world, p.rank, p.tiles_per_rank, p.gather = 99, -1, 1, n.MW_GATHER_PEER
+    assert lib.mw_tiles_create(C.byref(p), C.byref(h)) == n.MW_E_INVALID_ARG and b"world" in lib.mw_last_error()
+    p.world, p.rank = 2, 2
+    assert lib.mw_tiles_create(C.byref(p), C.byref(h)) == n.MW_E_INVALID_ARG and b"rank" in lib.mw_last_error()
+    p.rank, p.gather = 0, 7
+    assert lib.mw_tiles_create(C.byref(p), C.byref(h)) == n.MW_E_INVALID_ARG and b"gather" in lib.mw_last_error()
+    assert lib.mw_tiles_generate_allgather(None, 0.0, None) == n.MW_E_INVALID_ARG
+    assert lib.mw_tiles_export(None, None) == n.MW_E_INVALID_ARG
+    assert lib.mw_tiles_sync(None) == n.MW_E_INVALID_ARG
+    assert not lib.mw_tiles_ocean(None, 0)
+    lib.mw_tiles_destroy(None)  # no-op
+
+
+def test_tiles_struct_layouts_match_header(mw):
+    n = mw.native
+    assert C.sizeof(n.TilesParams) == 56 + 4 * 4 + 16 * 4 + 8 and n.TilesParams.devices.offset == 72
+    assert C.sizeof(n.TilesLayout) == 5 * 8 + 4 * 4
+    hdr = _header()
+    assert int(re.search(r"#define MW_TILES_BLOB_BYTES (\d+)", hdr).group(1)) == n.MW_TILES_BLOB_BYTES
+    assert int(re.search(r"#define MW_TILES_MAX_WORLD (\d+)", hdr).group(1)) == n.MW_TILES_MAX_WORLD
 
 
 def test_no_cpu_fallback_without_a_device(mw):

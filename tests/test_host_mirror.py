@@ -88,5 +88,25 @@ def test_bench_helpers_run_without_a_gpu(cref):
     args = argparse.Namespace(resolution=1024, tiles=16)
     one = bench.workload_config(args, 1)
     assert one["collective"] == "none" and one["algorithmic_bytes_per_point"] == 44 and one["parallelism"] == "tiles1"
-    assert "peer memory" in bench.workload_config(args, 8, "p2p")["collective"]
-    assert "NCCL" in bench.workload_config(args, 8, "nccl")["collective"]
+    many = argparse.Namespace(resolution=None, tiles=None)
+    bench.defaults_for_world(many, 8)
+    assert (many.resolution, many.tiles) == (2048, 1)            # N > 1 runs BASELINE configs[4]
+    cfg = bench.workload_config(many, 8, "peer")
+    assert "peer memory" in cfg["collective"] and "configs[4]" in cfg["workload"] and "117.4 MB" in cfg["workload"]
+    assert "ncclAllGather" in bench.workload_config(many, 8, "nccl")["collective"]
+    solo = argparse.Namespace(resolution=None, tiles=None)
+    bench.defaults_for_world(solo, 1)
+    assert (solo.resolution, solo.tiles) == (1024, 16)
+
+
+def test_bench_has_no_collective_under_a_rank_local_condition():
+    """Round-1 defect: a clock-sampler top-up loop with a rank-local trip count contained collectives and desynchronised
+    the ranks.  The loop that remains may only call generate_local (no collective inside)."""
+    import re
+    src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py")).read()
+    m = re.search(r"while len\(clk\.samples\) < 8 and extra < 200:(.*?)extra \+= 1", src, re.S)
+    assert m, "top-up loop not found"
+    body = m.group(1)
+    assert "generate_local" in body
+    for forbidden in ("generate_pipelined", "all_gather", "all_reduce", "barrier(", "generate("):
+        assert forbidden not in body, forbidden
