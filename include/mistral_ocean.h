@@ -250,11 +250,20 @@ typedef struct mw_gerstner_wave {
     float amp_y;        /* Gerstner: amp;             LevelOne: amp * amps[i]                  */
 } mw_gerstner_wave;
 
+/* mw_gerstner_params.flags, besides MW_DEVICE_PTRS: what out_nrm receives.  Default (neither bit): (0, 1, 0), what the
+ * reference ships -- both shader variants overwrite their normal with it (MistralWaterLib.cginc:98, :121). */
+enum {
+    MW_GERSTNER_NORMAL_ANALYTIC = 1u << 4,  /* the exact normal of the displaced surface P(x, z) = (x + offs.x, offs.y, z + offs.z):
+                                               normalize(dP/dz x dP/dx), from the same per-wave sin / cos -- what the commented
+                                               attempt at :122-124 was after                              */
+    MW_GERSTNER_NORMAL_DISCARDED = 1u << 5  /* the value Gerstner() computes at :92-97 and then throws away, literally:
+                                               n = (0, 2, 0); n.x -= offs.x; n.y -= offs.z; n.xz *= smoothing; normalize(n)     */
+};
 typedef struct mw_gerstner_params {
     int32_t n_waves;
     int32_t device;
-    uint32_t flags; /* MW_DEVICE_PTRS */
-    uint32_t reserved;
+    uint32_t flags;  /* MW_DEVICE_PTRS | MW_GERSTNER_NORMAL_* */
+    float smoothing; /* _Smoothing (MistralWaterLib.cginc:66), read by MW_GERSTNER_NORMAL_DISCARDED only */
     mw_gerstner_wave waves[MW_GERSTNER_MAX_WAVES];
 } mw_gerstner_params;
 
@@ -268,7 +277,8 @@ int mw_gerstner_append_level_one(mw_gerstner_params* p, float amplitude, float f
 /*
  * out_xyz[v] = pos_xyz[v] + offsets(pos_xyz[v].xz, t)   (MistralWaterLib.cginc:176)
  * out_nrm[v] = (0, 1, 0)  if non-NULL                   (:98 / :121 -- the reference discards
- *                                                        its computed normal)
+ *                                                        its computed normal), or the normal selected
+ *                                                        by MW_GERSTNER_NORMAL_* in p->flags
  * n vertices of packed float3.
  */
 int mw_gerstner_displace(const mw_gerstner_params* p, const float* pos_xyz, float* out_xyz, float* out_nrm,

@@ -34,9 +34,12 @@ __device__ __forceinline__ void sincos_reduced(float th, float* s, float* c)
 constexpr int VPT = 4;  // vertices per thread: 3 float4 in, 3 float4 out
 constexpr int THREADS = 256;
 
-template <bool NRM>
+// NRM: 0 = no normal output, 1 = (0, 1, 0) (what the reference ships, :98 / :121), 2 = analytic normal of the displaced
+// surface, 3 = the value Gerstner() computes at :92-97 before discarding it
+template <int NRM>
 __global__ void __launch_bounds__(THREADS) k_gerstner(const __grid_constant__ GerstnerTable tab, const float* __restrict__ pos,
-                                                      float* __restrict__ out, float* __restrict__ nrm, int64_t n, float t)
+                                                      float* __restrict__ out, float* __restrict__ nrm, int64_t n, float t,
+                                                      float smoothing)
 {
     const int64_t v0 = ((int64_t)blockIdx.x * THREADS + threadIdx.x) * VPT;
     if (v0 >= n) return;
@@ -54,8 +57,11 @@ __global__ void __launch_bounds__(THREADS) k_gerstner(const __grid_constant__ Ge
         for (int k = 0; k < VPT * 3; ++k) p[k] = (3 * v0 + k < 3 * n) ? pos[3 * v0 + k] : 0.f;
     }
     float ox[VPT], oy[VPT], oz[VPT];
+    // analytic normal: partial derivatives of P = (x + offs.x, offs.y, z + offs.z) with respect to the rest position
+    //   dP/dx = (1 - jxx, hx, -jxz), dP/dz = (-jxz, hz, 1 - jzz),  jab = sum amp_xz f Da Db sin, ha = sum amp_y f Da cos
+    float jxx[VPT], jxz[VPT], jzz[VPT], hx[VPT], hz[VPT];
 #pragma unroll
-    for (int v = 0; v < VPT; ++v) ox[v] = oy[v] = oz[v] = 0.f;
+    for (int v = 0; v < VPT; ++v) { ox[v] = oy[v] = oz[v] = 0.f; jxx[v] = jxz[v] = jzz[v] = hx[v] = hz[v] = 0.f; }
     const int nw = tab.n_waves;
 #pragma unroll 2
     for (int w = 0; w < nw; ++w) {
@@ -75,7 +81,32 @@ __global__ void __launch_bounds__(THREADS) k_gerstner(const __grid_constant__ Ge
             ox[v] = fmaf(ax, c, ox[v]);       // :86 / :114
             oz[v] = fmaf(az, c, oz[v]);       // :87 / :115
             oy[v] = fmaf(W.amp_y, s, oy[v]);  // :88 / :116
+            if (NRM == 2) {
+                const float fs = W.freq * s, fc = W.freq * c;
+                jxx[v] = fmaf(ax * W.dir_x, fs, jxx[v]);
+                jxz[v] = fmaf(ax * W.dir_y, fs, jxz[v]);
+                jzz[v] = fmaf(az * W.dir_y, fs, jzz[v]);
+                hx[v] = fmaf(W.amp_y * W.dir_x, fc, hx[v]);
+                hz[v] = fmaf(W.amp_y * W.dir_y, fc, hz[v]);
+            }
         }
+    }
+    float nv[VPT * 3];
+#pragma unroll
+    for (int v = 0; v < VPT; ++v) {
+        float nx = 0.f, ny = 1.f, nz = 0.f;
+        if (NRM == 2) {
+            // dP/dz x dP/dx (y up): a = dP/dz = (-jxz, hz, 1 - jzz), b = dP/dx = (1 - jxx, hx, -jxz)
+            const float a0 = -jxz[v], a1 = hz[v], a2 = 1.0f - jzz[v], b0 = 1.0f - jxx[v], b1 = hx[v], b2 = -jxz[v];
+            nx = a1 * b2 - a2 * b1; ny = a2 * b0 - a0 * b2; nz = a0 * b1 - a1 * b0;
+            const float inv = rsqrtf(nx * nx + ny * ny + nz * nz);
+            nx *= inv; ny *= inv; nz *= inv;
+        } else if (NRM == 3) {
+            nx = (0.0f - ox[v]) * smoothing; ny = 2.0f - oz[v]; nz = 0.0f * smoothing;  // :92-96
+            const float inv = rsqrtf(nx * nx + ny * ny + nz * nz);                       // :97 normalize
+            nx *= inv; ny *= inv; nz *= inv;
+        }
+        nv[3 * v + 0] = nx; nv[3 * v + 1] = ny; nv[3 * v + 2] = nz;
     }
 #pragma unroll
     for (int v = 0; v < VPT; ++v) { p[3 * v + 0] += ox[v]; p[3 * v + 1] += oy[v]; p[3 * v + 2] += oz[v]; }  // :176
@@ -83,17 +114,16 @@ __global__ void __launch_bounds__(THREADS) k_gerstner(const __grid_constant__ Ge
         float4* dst = reinterpret_cast<float4*>(out + 3 * v0);
 #pragma unroll
         for (int k = 0; k < 3; ++k) dst[k] = make_float4(p[4 * k + 0], p[4 * k + 1], p[4 * k + 2], p[4 * k + 3]);
-        if (NRM) {  // (0,1,0) x4 = 0 1 0 0 | 1 0 0 1 | 0 0 1 0   (:98, :121)
+        if (NRM) {  // mode 1: (0,1,0) x4 = 0 1 0 0 | 1 0 0 1 | 0 0 1 0   (:98, :121)
             float4* dn = reinterpret_cast<float4*>(nrm + 3 * v0);
-            dn[0] = make_float4(0.f, 1.f, 0.f, 0.f);
-            dn[1] = make_float4(1.f, 0.f, 0.f, 1.f);
-            dn[2] = make_float4(0.f, 0.f, 1.f, 0.f);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) dn[k] = make_float4(nv[4 * k + 0], nv[4 * k + 1], nv[4 * k + 2], nv[4 * k + 3]);
         }
     } else {
         for (int k = 0; k < VPT * 3; ++k)
             if (3 * v0 + k < 3 * n) {
                 out[3 * v0 + k] = p[k];
-                if (NRM) nrm[3 * v0 + k] = (k % 3 == 1) ? 1.f : 0.f;
+                if (NRM) nrm[3 * v0 + k] = nv[k];
             }
     }
 }
@@ -170,8 +200,10 @@ extern "C" int mw_gerstner_displace(const mw_gerstner_params* p, const float* po
     }
     const int64_t threads_needed = (n + VPT - 1) / VPT;
     const unsigned grid = (unsigned)((threads_needed + THREADS - 1) / THREADS);
-    if (d_nrm) k_gerstner<true><<<grid, THREADS, 0, st>>>(tab, d_pos, d_out, d_nrm, n, t);
-    else k_gerstner<false><<<grid, THREADS, 0, st>>>(tab, d_pos, d_out, nullptr, n, t);
+    if (!d_nrm) k_gerstner<0><<<grid, THREADS, 0, st>>>(tab, d_pos, d_out, nullptr, n, t, 0.f);
+    else if (p->flags & MW_GERSTNER_NORMAL_ANALYTIC) k_gerstner<2><<<grid, THREADS, 0, st>>>(tab, d_pos, d_out, d_nrm, n, t, 0.f);
+    else if (p->flags & MW_GERSTNER_NORMAL_DISCARDED) k_gerstner<3><<<grid, THREADS, 0, st>>>(tab, d_pos, d_out, d_nrm, n, t, p->smoothing);
+    else k_gerstner<1><<<grid, THREADS, 0, st>>>(tab, d_pos, d_out, d_nrm, n, t, 0.f);
     g_mw_launches.fetch_add(1, std::memory_order_relaxed);
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess && !dev) {

@@ -155,6 +155,7 @@ struct TileRank {
     int rank = -1, device = -1;
     mw_ocean* ocean = nullptr;
     cudaStream_t s_user_own = nullptr, s_user = nullptr, s_gen = nullptr, s_comm = nullptr;
+    cudaStream_t s_flag = nullptr;   // "my buffer is free" announcements: never queued behind a gather in progress
     cudaStream_t s_push[MAXW] = {};
     char* alloc = nullptr;           // [2][world][slot] floats + FlagWords
     float* gather[2] = {nullptr, nullptr};
@@ -216,6 +217,7 @@ int create_rank(mw_tiles* t, TileRank& r, int rank, int device)
     MW_CUDA(cudaStreamCreateWithFlags(&r.s_user_own, cudaStreamNonBlocking));
     MW_CUDA(cudaStreamCreateWithFlags(&r.s_gen, cudaStreamNonBlocking));
     MW_CUDA(cudaStreamCreateWithFlags(&r.s_comm, cudaStreamNonBlocking));
+    MW_CUDA(cudaStreamCreateWithFlags(&r.s_flag, cudaStreamNonBlocking));
     r.s_user = r.s_user_own;
     if ((rc = mw_ocean_set_stream(r.ocean, r.s_gen))) return rc;
     for (int p = 0; p < t->world; ++p) {
@@ -238,7 +240,7 @@ void destroy_rank(mw_tiles* t, TileRank& r)
 {
     if (r.device < 0) return;
     cudaSetDevice(r.device);
-    cudaStream_t all[] = {r.s_gen, r.s_comm, r.s_user_own};
+    cudaStream_t all[] = {r.s_gen, r.s_comm, r.s_flag, r.s_user_own};
     for (cudaStream_t s : all) if (s) cudaStreamSynchronize(s);
     for (int p = 0; p < MAXW; ++p) if (r.s_push[p]) cudaStreamSynchronize(r.s_push[p]);
     if (r.comm && nccl_api()->ok) nccl_api()->CommDestroy(r.comm);
@@ -561,11 +563,15 @@ int enqueue_gather(mw_tiles* t, int b)
     }
     const uint32_t seq = ++t->gathers;
     const size_t slot_bytes = t->slot_floats * sizeof(float);
-    // the user stream's position at this call bounds the readers of buffer b that the gather must not overtake
+    // The user stream's position at this call bounds the readers of buffer b that the gather must not overtake.  The
+    // "free" announcement travels on its own stream: it must not queue behind the previous gather's completion waits on
+    // s_comm, or every step would pay a flag round trip between two gathers.  (Announcing before the previous gather into
+    // this buffer has completed is safe: a peer's pushes into it are ordered on that peer's push stream.)
     for (auto& r : t->ranks) {
         MW_CUDA(cudaSetDevice(r.device));
         MW_CUDA(cudaEventRecord(r.ev_user, r.s_user));
         MW_CUDA(cudaStreamWaitEvent(r.s_comm, r.ev_user, 0));
+        MW_CUDA(cudaStreamWaitEvent(r.s_flag, r.ev_user, 0));
     }
     if (t->impl == MW_GATHER_NCCL) {
         NcclApi* n = nccl_api();
@@ -583,7 +589,7 @@ int enqueue_gather(mw_tiles* t, int b)
         // phase 1: every rank's buffer b is free of readers from here on (its user stream has been waited for)
         for (auto& r : t->ranks) {
             MW_CUDA(cudaSetDevice(r.device));
-            MW_CUDA(cudaEventRecord(r.ev_free[b], r.s_comm));
+            MW_CUDA(cudaEventRecord(r.ev_free[b], r.s_flag));
         }
         // phase 2: pushes, one copy-engine stream per (source, destination); destinations visited in a rank-dependent order
         for (auto& r : t->ranks) {
@@ -614,10 +620,10 @@ int enqueue_gather(mw_tiles* t, int b)
         MemOps* m = memops();
         TileRank& r = t->ranks[0];
         MW_CUDA(cudaSetDevice(r.device));
-        // my buffer b is free of readers: tell every peer (ordered after ev_user on s_comm)
+        // my buffer b is free of readers: tell every peer (ordered after ev_user on s_flag)
         for (int j = 1; j < t->world; ++j) {
             const int p = (r.rank + j) % t->world;
-            int rc = flag_write(t, r.s_comm, &r.peer_flags[p]->free_[b][r.rank], seq);
+            int rc = flag_write(t, r.s_flag, &r.peer_flags[p]->free_[b][r.rank], seq);
             if (rc) return rc;
         }
         const float* src = r.gather[b] + (size_t)r.rank * t->slot_floats;
@@ -719,6 +725,7 @@ extern "C" int mw_tiles_sync(mw_tiles* t)
     for (auto& r : t->ranks) {
         MW_CUDA(cudaSetDevice(r.device));
         MW_CUDA(cudaStreamSynchronize(r.s_gen));
+        MW_CUDA(cudaStreamSynchronize(r.s_flag));
         for (int p = 0; p < MAXW; ++p) if (r.s_push[p]) MW_CUDA(cudaStreamSynchronize(r.s_push[p]));
         MW_CUDA(cudaStreamSynchronize(r.s_comm));
         if (r.comm) {

@@ -20,6 +20,8 @@ MW_DEVICE_PTRS = 1 << 0
 MW_PROFILE = 1 << 1
 MW_WRAP_REPEAT = 1 << 2
 MW_HOST_ASYNC = 1 << 3
+MW_GERSTNER_NORMAL_ANALYTIC = 1 << 4
+MW_GERSTNER_NORMAL_DISCARDED = 1 << 5
 MW_KERNEL_COUNT = 3
 MW_GERSTNER_MAX_WAVES = 64
 
@@ -97,7 +99,7 @@ class GerstnerWave(C.Structure):
 
 
 class GerstnerParams(C.Structure):
-    _fields_ = [("n_waves", C.c_int32), ("device", C.c_int32), ("flags", C.c_uint32), ("reserved", C.c_uint32),
+    _fields_ = [("n_waves", C.c_int32), ("device", C.c_int32), ("flags", C.c_uint32), ("smoothing", C.c_float),
                 ("waves", GerstnerWave * MW_GERSTNER_MAX_WAVES)]
 
 

@@ -60,11 +60,17 @@ class GerstnerWaves:
         return np.array([[w.dir_x, w.dir_y, w.freq, w.rate, w.amp_xz, w.amp_y]
                          for w in self.p.waves[: self.p.n_waves]], np.float32).reshape(-1, 6)
 
-    def displace(self, pos, t: float, out=None, normals=None, stream: int = 0):
-        """v.vertex.xyz += offsets (MistralWaterLib.cginc:176).  pos/out: [n, 3] float32."""
+    def displace(self, pos, t: float, out=None, normals=None, stream: int = 0, normal_mode: str = "up", smoothing: float = 1.0):
+        """v.vertex.xyz += offsets (MistralWaterLib.cginc:176).  pos/out: [n, 3] float32.
+        normals (optional [n, 3] buffer) receives, by normal_mode: "up" = (0, 1, 0), what the shader ships (:98, :121);
+        "analytic" = the displaced surface's own normal (what the commented lines :122-124 were after); "discarded" = the
+        value Gerstner() computes at :92-97 and then overwrites (uses _Smoothing)."""
         n = int(pos.shape[0])
         if out is None:
             out = np.empty_like(pos)
+        bits = {"up": 0, "analytic": native.MW_GERSTNER_NORMAL_ANALYTIC, "discarded": native.MW_GERSTNER_NORMAL_DISCARDED}[normal_mode]
+        self.p.flags = (self.p.flags & ~(native.MW_GERSTNER_NORMAL_ANALYTIC | native.MW_GERSTNER_NORMAL_DISCARDED)) | bits
+        self.p.smoothing = float(smoothing)
         check(self._lib.mw_gerstner_displace(C.byref(self.p), _addr(pos), _addr(out), _addr(normals) or None,
                                              n, float(t), C.c_void_p(stream)))
         return out

@@ -49,6 +49,7 @@ def lib():
         _lib.ref_gerstner4.argtypes = [fp, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, fp, fp, fp, fp]
         _lib.ref_gerstner_level_one.argtypes = [fp, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, fp]
         _lib.ref_gerstner_table.argtypes = [fp, C.c_int, fp, C.c_int64, C.c_float, fp, fp]
+        _lib.ref_gerstner_table_normals.argtypes = [fp, C.c_int, fp, C.c_int64, C.c_float, C.c_int, C.c_float, fp]
         _lib.ref_wave.argtypes = [fp, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, fp, fp]
     return _lib
 
@@ -169,6 +170,17 @@ def gerstner_table(waves, pos, t, want_normal=False):
     nrm = np.empty_like(pos) if want_normal else None
     lib().ref_gerstner_table(_p(waves), waves.shape[0], _p(pos), pos.shape[0], t, _p(out), _p(nrm))
     return (out, nrm) if want_normal else out
+
+
+def gerstner_table_normals(waves, pos, t, mode="analytic", smoothing=1.0):
+    """The normals the reference computes but does not ship: "analytic" (the displaced surface's own normal, what
+    MistralWaterLib.cginc:122-124 was after) or "discarded" (Gerstner() :92-97 literally)."""
+    pos = _f32(pos)
+    waves = _f32(waves).reshape(-1, 6)
+    nrm = np.empty_like(pos)
+    lib().ref_gerstner_table_normals(_p(waves), waves.shape[0], _p(pos), pos.shape[0], t, {"analytic": 2, "discarded": 3}[mode],
+                                     smoothing, _p(nrm))
+    return nrm
 
 
 def wave(pos, t, amplitude, frequency, speed, smoothing):

@@ -105,6 +105,54 @@ void ref_gerstner_table(const float* waves, int n_waves, const float* pos_xyz, i
     }
 }
 
+/*
+ * The two normals the reference has code for but does not ship (both variants end with normal = (0, 1, 0), :98 / :121):
+ *   mode 2 "analytic":  the exact normal of the displaced surface P(x, z) = (x + offs.x, offs.y, z + offs.z) the table form
+ *                       defines, normalize(dP/dz x dP/dx) -- what the commented attempt at :122-124 was after; evaluated in
+ *                       double here (it is a derived quantity, parity is a tolerance);
+ *   mode 3 "discarded": Gerstner() :92-97 literally, fp32 in source order:
+ *                       normal = (0,2,0); normal.x -= offs.x; normal.y -= offs.z; normal.xz *= _Smoothing; normalize.
+ */
+void ref_gerstner_table_normals(const float* waves, int n_waves, const float* pos_xyz, int64_t n, float t, int mode,
+                                float smoothing, float* out_nrm)
+{
+    for (int64_t v = 0; v < n; ++v) {
+        float sx = pos_xyz[3 * v + 0], sz = pos_xyz[3 * v + 2];
+        if (mode == 3) {
+            float ox = 0.f, oz = 0.f;
+            for (int w = 0; w < n_waves; ++w) {
+                const float* W = waves + 6 * w;
+                float th = W[2] * (W[0] * sx + W[1] * sz) + W[3] * t;
+                float c = fcos(th);
+                ox += W[4] * W[0] * c;
+                oz += W[4] * W[1] * c;
+            }
+            float nx = 0.f, ny = 2.f, nz = 0.f;
+            nx -= ox;
+            ny -= oz;
+            nx *= smoothing; nz *= smoothing;
+            float len = (float)sqrt((double)(nx * nx + ny * ny + nz * nz));
+            out_nrm[3 * v + 0] = nx / len; out_nrm[3 * v + 1] = ny / len; out_nrm[3 * v + 2] = nz / len;
+        } else {
+            double jxx = 0, jxz = 0, jzz = 0, hx = 0, hz = 0;
+            for (int w = 0; w < n_waves; ++w) {
+                const float* W = waves + 6 * w;
+                float th = W[2] * (W[0] * sx + W[1] * sz) + W[3] * t;   /* the same fp32 phase the displacement uses */
+                double s = sin((double)th), c = cos((double)th), f = W[2];
+                jxx += (double)W[4] * W[0] * W[0] * f * s;
+                jxz += (double)W[4] * W[0] * W[1] * f * s;
+                jzz += (double)W[4] * W[1] * W[1] * f * s;
+                hx += (double)W[5] * W[0] * f * c;
+                hz += (double)W[5] * W[1] * f * c;
+            }
+            double a[3] = {-jxz, hz, 1.0 - jzz}, b[3] = {1.0 - jxx, hx, -jxz};
+            double c3[3] = {a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]};
+            double len = sqrt(c3[0] * c3[0] + c3[1] * c3[1] + c3[2] * c3[2]);
+            out_nrm[3 * v + 0] = (float)(c3[0] / len); out_nrm[3 * v + 1] = (float)(c3[1] / len); out_nrm[3 * v + 2] = (float)(c3[2] / len);
+        }
+    }
+}
+
 /* MistralWaterLib.cginc:127-152 Wave + its call site Displacement :160-164 (keyword _DISPLACEMENTMODE_WAVE), with
  * unity_ObjectToWorld = unity_WorldToObject = identity (a pond mesh placed at the origin, unrotated, unscaled):
  *   sVertex = worldPos = vertex;  out.y = vertex.y + offsets.y  where offsets = displaced v0 (so out.y = 2 y + wave);

@@ -109,3 +109,44 @@ def test_wave_mode_matches_literal(mw, cref, n):
     assert np.abs(gn - wn).max() <= 2e-3 and np.abs(np.linalg.norm(gn, axis=1) - 1).max() <= 1e-5
     only, none = mw.wave_displace(pos, 12.5, 10.0, 2.58, 1.3, 0.4, want_normal=False)
     assert none is None and np.array_equal(only, got)
+
+
+@pytest.mark.parametrize("n", [1, 7, 4096 + 3])
+def test_analytic_and_discarded_normals(mw, cref, n):
+    """the normals the reference has code for but overwrites with (0,1,0) (MistralWaterLib.cginc:92-98,
+    :122-124).  Tolerance: per-wave sin/cos error 5e-7 times the summed derivative amplitudes, after normalisation."""
+    rng = np.random.default_rng(5)
+    pos = (rng.uniform(-40, 40, (n, 3))).astype(np.float32)
+    gw = mw.pond_wave_table_32()
+    tab = gw.table()
+    t = 1.7
+    nrm = np.empty_like(pos)
+    out = gw.displace(pos, t, normals=nrm, normal_mode="analytic")
+    want = cref.gerstner_table_normals(tab, pos, t, "analytic")
+    amp = float(np.sum((np.abs(tab[:, 4]) + np.abs(tab[:, 5])) * np.abs(tab[:, 2]) * np.hypot(tab[:, 0], tab[:, 1]) ** 2))
+    assert np.abs(nrm - want).max() <= 4e-6 * max(1.0, amp)
+    assert np.allclose(np.linalg.norm(nrm, axis=1), 1.0, atol=1e-6) and (nrm[:, 1] > 0).all()
+    assert np.abs(out - cref.gerstner_table(tab, pos, t)).max() <= _tol(tab, pos)      # the displacement is unchanged
+    # finite-difference check of what "analytic" means: the normal of the displaced surface itself
+    if n == 7:
+        h = 1e-3
+        p64 = pos.astype(np.float64)
+        def surf(p):
+            th = tab[:, 2].astype(np.float64) * (p[:, None, 0] * tab[:, 0] + p[:, None, 2] * tab[:, 1]) + tab[:, 3].astype(np.float64) * t
+            o = np.stack([(tab[:, 4] * tab[:, 0] * np.cos(th)).sum(1), (tab[:, 5] * np.sin(th)).sum(1), (tab[:, 4] * tab[:, 1] * np.cos(th)).sum(1)], 1)
+            return p + o
+        dx = (surf(p64 + [h, 0, 0]) - surf(p64 - [h, 0, 0])) / (2 * h)
+        dz = (surf(p64 + [0, 0, h]) - surf(p64 - [0, 0, h])) / (2 * h)
+        fd = np.cross(dz, dx)
+        fd /= np.linalg.norm(fd, axis=1, keepdims=True)
+        assert np.abs(fd - want).max() < 1e-4
+    # the literal discarded computation of Gerstner() :92-97, with _Smoothing
+    nrm2 = np.empty_like(pos)
+    gw.displace(pos, t, normals=nrm2, normal_mode="discarded", smoothing=0.35)
+    want2 = cref.gerstner_table_normals(tab, pos, t, "discarded", 0.35)
+    assert np.abs(nrm2 - want2).max() <= 4e-6
+    assert np.all(nrm2[:, 2] == 0.0)
+    # and the shipped behaviour stays the default
+    nrm3 = np.empty_like(pos)
+    gw.displace(pos, t, normals=nrm3)
+    assert np.array_equal(nrm3, np.tile(np.float32([0, 1, 0]), (n, 1)))
