@@ -3,7 +3,10 @@
 // Drop this file next to Assets/Mistral Water/Scripts/FFTMesh.cs and put the shared library where Unity's
 // native-plugin loader finds it (Assets/Plugins/x86_64/libmistral_ocean.so).  It could not be compiled in the
 // build image (no dotnet / mono / Unity there); the same exported symbols are exercised through ctypes by
-// mistral-water_b200/native.py and tests/.  Struct layouts are asserted in tests/test_abi.py.
+// mistral-water_b200/native.py and tests/.  Struct layouts are asserted in tests/test_abi.py, and
+// bindings/MistralOcean.Bindings.csproj compiles this file WITHOUT Unity (bindings/UnityShim.cs stands in for the
+// four UnityEngine types used here) together with bindings/LayoutCheck.cs, which prints Marshal.SizeOf / OffsetOf of
+// every struct next to the values the C header gives: `dotnet run --project bindings` on any machine with the SDK.
 using System;
 using System.Runtime.InteropServices;
 using UnityEngine;
@@ -46,7 +49,8 @@ namespace MistralWater.Native
     public struct MwGerstnerParams
     {
         public int nWaves, device;
-        public uint flags, reserved;
+        public uint flags;                 // MW_DEVICE_PTRS = 1, MW_GERSTNER_NORMAL_ANALYTIC = 16, MW_GERSTNER_NORMAL_DISCARDED = 32
+        public float smoothing;            // _Smoothing (MistralWaterLib.cginc:66), for MW_GERSTNER_NORMAL_DISCARDED
         [MarshalAs(UnmanagedType.ByValArray, SizeConst = 64)] public MwGerstnerWave[] waves;
     }
 
@@ -74,6 +78,26 @@ namespace MistralWater.Native
         public IntPtr white;               // float[]  -> _White.r (:312)
         public IntPtr whiteRgba;           // Color[]  (xx, xx, xx, 1)
         public IntPtr jacobian;            // float[]
+    }
+
+    [StructLayout(LayoutKind.Sequential)]
+    public struct MwTilesParams            // mw_tiles_params: multi-GPU tile sets (no reference counterpart; SURVEY.md section 8e)
+    {
+        public MwOceanParams ocean;        // per-tile parameters (.tiles / .device ignored)
+        public int world;                  // ranks = GPUs
+        public int rank;                   // -1: this process drives every GPU (the Unity host model)
+        public int tilesPerRank;
+        public int gather;                 // MW_GATHER_NCCL = 0, MW_GATHER_PEER = 1
+        [MarshalAs(UnmanagedType.ByValArray, SizeConst = 16)] public int[] devices;
+        public float windStepDeg;          // config 5: 45
+        public uint flags;                 // MW_TILES_ASYNC = 1
+    }
+
+    [StructLayout(LayoutKind.Sequential)]
+    public struct MwTilesLayout            // mw_tiles_layout
+    {
+        public long slotFloats, heightOff, dispOff, normalOff, whitecapOff;
+        public int world, tilesPerRank, resolution, localRanks;
     }
 
     [StructLayout(LayoutKind.Sequential)]
@@ -127,11 +151,24 @@ namespace MistralWater.Native
         [DllImport(Lib)] public static extern int mw_wave_displace(ref MwWaveParams p, IntPtr posXyz, IntPtr outXyz, IntPtr outNrm,
             long n, float t, IntPtr cudaStream);
 
-        // multi-GPU tile sets, one process per GPU (no reference counterpart): CUDA IPC peer mappings + copy-engine pushes
-        [DllImport(Lib)] public static extern int mw_peer_export(IntPtr devPtr, byte[] handle64, out ulong offset);
-        [DllImport(Lib)] public static extern int mw_peer_open(int device, byte[] handle64, out IntPtr basePtr);
-        [DllImport(Lib)] public static extern int mw_peer_close(int device, IntPtr basePtr);
-        [DllImport(Lib)] public static extern int mw_peer_copy(IntPtr dst, IntPtr src, ulong bytes, IntPtr cudaStream);
+        // multi-GPU tile sets (no reference counterpart): the handle owns gather buffers, streams, peer mappings and NCCL
+        // communicators; rank = -1 drives all GPUs from this one process (ncclCommInitAll / peer copies fenced by events)
+        public const int MW_GATHER_NCCL = 0, MW_GATHER_PEER = 1, MW_TILES_BLOB_BYTES = 512;
+        [DllImport(Lib)] public static extern int mw_tiles_create(ref MwTilesParams p, out IntPtr handle);
+        [DllImport(Lib)] public static extern void mw_tiles_destroy(IntPtr handle);
+        [DllImport(Lib)] public static extern int mw_tiles_get_layout(IntPtr handle, out MwTilesLayout layout);
+        [DllImport(Lib)] public static extern int mw_tiles_export(IntPtr handle, byte[] blob512);
+        [DllImport(Lib)] public static extern int mw_tiles_connect(IntPtr handle, byte[] blobsInRankOrder);
+        [DllImport(Lib)] public static extern int mw_tiles_init_spectrum(IntPtr handle);
+        [DllImport(Lib)] public static extern int mw_tiles_set_h0(IntPtr handle, int localRank, IntPtr h0Device, IntPtr h0conjDevice);
+        [DllImport(Lib)] public static extern int mw_tiles_set_stream(IntPtr handle, IntPtr[] cudaStreams);
+        [DllImport(Lib)] public static extern int mw_tiles_generate_allgather(IntPtr handle, float time, IntPtr[] gathered);
+        [DllImport(Lib)] public static extern int mw_tiles_generate_local(IntPtr handle, float time, IntPtr[] gathered);
+        [DllImport(Lib)] public static extern int mw_tiles_allgather(IntPtr handle);
+        [DllImport(Lib)] public static extern int mw_tiles_wait(IntPtr handle, int framesBack);
+        [DllImport(Lib)] public static extern int mw_tiles_sync(IntPtr handle);
+        [DllImport(Lib)] public static extern int mw_tiles_gather_impl(IntPtr handle);
+        [DllImport(Lib)] public static extern IntPtr mw_tiles_ocean(IntPtr handle, int localRank);
 
         public static void Check(int rc) { if (rc != MW_OK) throw new InvalidOperationException("mistral_ocean " + rc + ": " + LastError()); }
     }
@@ -171,6 +208,32 @@ namespace MistralWater.Native
             if (handle != IntPtr.Zero) { MistralOcean.mw_renderer_destroy(handle); handle = IntPtr.Zero; }
             if (hd.IsAllocated) hd.Free(); if (hh.IsAllocated) hh.Free(); if (hn.IsAllocated) hn.Free(); if (hw.IsAllocated) hw.Free();
         }
+    }
+
+    // BASELINE config 5 from ONE host process: `world` GPUs, one independent tile each, every GPU ends with every tile
+    // (device memory: the returned pointers are for CUDA-side consumers, e.g. graphics interop).
+    public sealed class TileSetEngine : IDisposable
+    {
+        IntPtr handle;
+        public readonly MwTilesLayout layout;
+        public readonly IntPtr[] gathered;               // per GPU: [world][slotFloats] floats of the latest frame
+
+        public TileSetEngine(int world, int resolution, float unitWidth, float choppiness, float amplitude, Vector2 wind, ulong seed,
+                             bool nccl = false)
+        {
+            var p = new MwTilesParams { ocean = new MwOceanParams { resolution = resolution, unitWidth = unitWidth,
+                length = resolution * unitWidth, choppiness = choppiness, amplitude = amplitude, windX = wind.x, windY = wind.y,
+                tDivision = 1f, seed = seed, tiles = 1 }, world = world, rank = -1, tilesPerRank = 1,
+                gather = nccl ? MistralOcean.MW_GATHER_NCCL : MistralOcean.MW_GATHER_PEER, devices = new int[16], windStepDeg = 45f };
+            for (int i = 0; i < world; ++i) p.devices[i] = i;
+            MistralOcean.Check(MistralOcean.mw_tiles_create(ref p, out handle));
+            MistralOcean.Check(MistralOcean.mw_tiles_get_layout(handle, out layout));
+            MistralOcean.Check(MistralOcean.mw_tiles_init_spectrum(handle));
+            gathered = new IntPtr[world];
+        }
+
+        public void GenerateAllGather(float t) { MistralOcean.Check(MistralOcean.mw_tiles_generate_allgather(handle, t, gathered)); }
+        public void Dispose() { if (handle != IntPtr.Zero) { MistralOcean.mw_tiles_destroy(handle); handle = IntPtr.Zero; } }
     }
 
     // The substitution inside FFTMesh.cs (see INTEGRATION.md): bodies of SetParams / GenerateMesh / EvaluateWaves.

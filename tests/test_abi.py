@@ -123,3 +123,23 @@ def test_product_never_imports_the_oracle():
                 txt = open(os.path.join(dp, fn)).read()
                 assert "oracle" not in txt.replace("oracle/ is", ""), f"{fn} mentions the oracle"
                 assert "import cref" not in txt and "ref_fft64" not in txt
+
+
+def test_csharp_binding_declares_every_symbol_and_layout(mw):
+    """bindings/MistralOceanNative.cs cannot be compiled here (no dotnet); what can be checked is that it declares every
+    exported symbol and that LayoutCheck.cs expects the sizes the ctypes mirror has."""
+    n = mw.native
+    cs = open(os.path.join(ROOT, "bindings", "MistralOceanNative.cs")).read()
+    declared = set(re.findall(r"static extern \w+ (mw_[a-z0-9_]+)\(", cs))
+    assert declared == set(n.EXPORTS), sorted(set(n.EXPORTS) ^ declared)
+    chk = open(os.path.join(ROOT, "bindings", "LayoutCheck.cs")).read()
+    want = {"MwOceanParams": n.OceanParams, "MwOceanOut": n.OceanOut, "MwGerstnerWave": n.GerstnerWave,
+            "MwGerstnerParams": n.GerstnerParams, "MwRendererParams": n.RendererParams, "MwRendererOut": n.RendererOut,
+            "MwWaveParams": n.WaveParams, "MwTilesParams": n.TilesParams, "MwTilesLayout": n.TilesLayout}
+    for name, ct in want.items():
+        m = re.search(r"Marshal\.SizeOf\(typeof\(%s\)\), ([0-9 +*]+)\)" % name, chk)
+        assert m, name
+        assert eval(m.group(1)) == C.sizeof(ct), name
+    proj = open(os.path.join(ROOT, "bindings", "MistralOcean.Bindings.csproj")).read()
+    for f in ("MistralOceanNative.cs", "UnityShim.cs", "LayoutCheck.cs"):
+        assert f in proj
