@@ -19,9 +19,12 @@
  *   - buffer arguments are HOST pointers unless the handle was created with MW_DEVICE_PTRS,
  *     in which case they are device pointers on the handle's device and the call is
  *     asynchronous on the handle's stream (mw_ocean_sync to wait);
- *   - the engine supports the periodic case only: resolution a power of two in [32, 2048] and
- *     length == resolution * unit_width.  Anything else is
- *     MW_E_INVALID_ARG -- there is no CPU or O(N^4) fallback.
+ *   - the transform path covers the periodic case: resolution a power of two in [32, 2048] and
+ *     length == resolution * unit_width (only then is FFTMesh.Displacement's
+ *     direct sum a DFT).  Small grids outside it -- any resolution in [2, MW_DIRECT_MAX_RESOLUTION],
+ *     any length, e.g. the FFT Mesh demo scene's own 12 x 12 / 12.39 (Demo/FFT Mesh.unity:147,150) --
+ *     run the same sum directly ON THE GPU, one thread block per vertex (O(N^4) work, sized for what
+ *     the reference's CPU loop can run at all).  Anything else is MW_E_INVALID_ARG.  There is no CPU path.
  */
 #ifndef MISTRAL_OCEAN_H
 #define MISTRAL_OCEAN_H
@@ -35,7 +38,8 @@ extern "C" {
 #pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden */
 #endif
 
-#define MW_VERSION 100 /* 0.1.0 */
+#define MW_VERSION 200 /* 0.2.0 */
+#define MW_DIRECT_MAX_RESOLUTION 256 /* largest grid the direct-sum path accepts */
 
 enum {
     MW_OK = 0,

@@ -6,6 +6,7 @@
 #include <vector>
 
 #include "mw_ocean_kernels.cuh"
+#include "mw_direct_kernels.cuh"
 
 // ---------------------------------------------------------------------------------------------
 // error text (thread-local) and global launch counter
@@ -37,6 +38,8 @@ struct mw_ocean {
     bool device_ptrs = false;
     bool profile = false;
     bool have_h0 = false;
+    bool direct = false;                  // direct-sum frame (non-periodic / non-power-of-two / N < 32 grids): mw_direct_kernels.cuh
+    float2* dH = nullptr;                 // [tiles][N*N] htilde(t) of the frame (direct mode)
     bool host_async = false;              // MW_HOST_ASYNC: host-pointer calls do not wait
     cudaStream_t copy_stream = nullptr;   // device -> host result copies (host-pointer mode)
     cudaEvent_t ev_computed = nullptr, ev_copied = nullptr;
@@ -126,20 +129,25 @@ extern "C" int mw_ocean_create(const mw_ocean_params* params, mw_ocean** out)
     if (!params || !out) { mw_set_error("mw_ocean_create: null argument"); return MW_E_INVALID_ARG; }
     *out = nullptr;
     const mw_ocean_params& p = *params;
-    if (!is_pow2(p.resolution) || p.resolution < 32 || p.resolution > 2048) {
-        mw_set_error("resolution must be a power of two in [32, 2048], got %d (no O(N^4) fallback exists)", p.resolution);
-        return MW_E_INVALID_ARG;
-    }
     if (!(p.unit_width > 0.f) || !(p.length > 0.f) || !isfinite(p.unit_width) || !isfinite(p.length)) {
         mw_set_error("unit_width and length must be positive and finite");
         return MW_E_INVALID_ARG;
     }
-    {
-        const float want = (float)p.resolution * p.unit_width;
-        if (fabsf(p.length - want) > 1e-6f * fabsf(want)) {
-            mw_set_error("length (%g) must equal resolution * unit_width (%g): only the periodic case is an FFT", p.length, want);
-            return MW_E_INVALID_ARG;
-        }
+    // The transform path needs the periodic case (length == resolution * unit_width: only then is the reference's direct sum a
+    // DFT) on a power-of-two grid of 32..2048.  Small grids that are not (the FFT Mesh scene's own 12 x 12,
+    // length 12.39) run the same sum directly on the GPU (mw_direct_kernels.cuh); large ones are refused.
+    const float want_len = (float)p.resolution * p.unit_width;
+    const bool periodic = fabsf(p.length - want_len) <= 1e-6f * fabsf(want_len);
+    const bool fft_ok = is_pow2(p.resolution) && p.resolution >= 32 && p.resolution <= 2048 && periodic;
+    const bool direct = !fft_ok;
+    if (direct && (p.resolution < 2 || p.resolution > MW_DIRECT_MAX_RESOLUTION)) {
+        if (!is_pow2(p.resolution) || p.resolution > 2048 || p.resolution < 2)
+            mw_set_error("resolution must be a power of two in [32, 2048] (transform path) or any value in [2, %d] (direct-sum path), got %d",
+                         MW_DIRECT_MAX_RESOLUTION, p.resolution);
+        else
+            mw_set_error("length (%g) must equal resolution * unit_width (%g) above resolution %d: only the periodic case is an FFT",
+                         p.length, want_len, MW_DIRECT_MAX_RESOLUTION);
+        return MW_E_INVALID_ARG;
     }
     if (p.tiles < 1 || p.tiles > 65535) { mw_set_error("tiles must be in [1, 65535], got %d", p.tiles); return MW_E_INVALID_ARG; }
     if (!(p.t_division != 0.f)) { mw_set_error("t_division must be non-zero"); return MW_E_INVALID_ARG; }
@@ -164,6 +172,7 @@ extern "C" int mw_ocean_create(const mw_ocean_params* params, mw_ocean** out)
     o->device_ptrs = (p.flags & MW_DEVICE_PTRS) != 0;
     o->profile = (p.flags & MW_PROFILE) != 0;
     o->host_async = (p.flags & MW_HOST_ASYNC) != 0 && !o->device_ptrs;
+    o->direct = direct;
     const int N = o->N;
     int rc = MW_OK;
     auto fail = [&](int code) { mw_ocean_destroy(o); return code; };
@@ -179,9 +188,18 @@ extern "C" int mw_ocean_create(const mw_ocean_params* params, mw_ocean** out)
         }
     }
     if ((rc = ensure(&o->spec, o->n2 * o->tiles))) return fail(rc);
-    if ((rc = ensure(&o->spec_r, o->n2 * o->tiles))) return fail(rc);
     if ((rc = ensure(&o->omega, o->n2))) return fail(rc);
     if ((rc = ensure(&o->qidx, o->n2))) return fail(rc);
+    if (direct) {
+        // direct-sum path: the spectrum as given, the per-frame htilde(t) image, omega; none of the transform's tables
+        if ((rc = ensure(&o->dH, o->n2 * o->tiles))) return fail(rc);
+        mwk::k_dispersion<<<(unsigned)((o->n2 + 255) / 256), 256, 0, o->stream>>>(o->omega, o->qidx, N, p.length);
+        g_mw_launches.fetch_add(1);
+        if (cudaStreamSynchronize(o->stream) != cudaSuccess) { mw_set_error("k_dispersion failed: %s", cudaGetErrorString(cudaGetLastError())); return fail(MW_E_CUDA); }
+        *out = o;
+        return MW_OK;
+    }
+    if ((rc = ensure(&o->spec_r, o->n2 * o->tiles))) return fail(rc);
     if ((rc = ensure(&o->ramp, (size_t)2 * N))) return fail(rc);
     if ((rc = ensure(&o->kd, (size_t)N))) return fail(rc);
     if ((rc = ensure(&o->tw, (size_t)N))) return fail(rc);
@@ -266,7 +284,7 @@ extern "C" void mw_ocean_destroy(mw_ocean* o)
     if (o->ev_computed) cudaEventDestroy(o->ev_computed);
     if (o->ev_copied) cudaEventDestroy(o->ev_copied);
     for (auto& e : o->ev_pool) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
-    void* ptrs[] = {o->s_stage, o->spec, o->spec_r, o->qidx, o->ptab, o->twimg, o->omega, o->ramp, o->kd, o->tw, o->XAB, o->s_height, o->s_disp, o->s_normal,
+    void* ptrs[] = {o->dH, o->s_stage, o->spec, o->spec_r, o->qidx, o->ptab, o->twimg, o->omega, o->ramp, o->kd, o->tw, o->XAB, o->s_height, o->s_disp, o->s_normal,
                     o->s_white, o->s_jac, o->s_vert, o->s_col, o->s_h};
     for (void* q : ptrs) if (q) cudaFree(q);
     for (int i = 0; i < 3; ++i) {
@@ -310,8 +328,10 @@ extern "C" int mw_ocean_init_spectrum(mw_ocean* o)
     mwk::k_init_spectrum<<<(unsigned)((total + 127) / 128), 128, 0, o->stream>>>(
         o->spec, o->N, o->tiles, o->p.length, o->p.amplitude, o->p.wind_x, o->p.wind_y, o->p.seed);
     MW_LAUNCH_CHECK();
-    mwk::k_ramp_spectrum<<<(unsigned)((total + 255) / 256), 256, 0, o->stream>>>(o->spec, o->ramp, o->spec_r, o->N, (int64_t)total);
-    MW_LAUNCH_CHECK();
+    if (!o->direct) {
+        mwk::k_ramp_spectrum<<<(unsigned)((total + 255) / 256), 256, 0, o->stream>>>(o->spec, o->ramp, o->spec_r, o->N, (int64_t)total);
+        MW_LAUNCH_CHECK();
+    }
     if (!o->device_ptrs) MW_CUDA(cudaStreamSynchronize(o->stream));
     o->have_h0 = true;
     return MW_OK;
@@ -334,8 +354,10 @@ extern "C" int mw_ocean_set_h0(mw_ocean* o, const float* h0, const float* h0conj
     }
     mwk::k_pack_h0<<<(unsigned)((total + 255) / 256), 256, 0, o->stream>>>(o->spec, d0, d1, (int64_t)total);
     MW_LAUNCH_CHECK();
-    mwk::k_ramp_spectrum<<<(unsigned)((total + 255) / 256), 256, 0, o->stream>>>(o->spec, o->ramp, o->spec_r, o->N, (int64_t)total);
-    MW_LAUNCH_CHECK();
+    if (!o->direct) {
+        mwk::k_ramp_spectrum<<<(unsigned)((total + 255) / 256), 256, 0, o->stream>>>(o->spec, o->ramp, o->spec_r, o->N, (int64_t)total);
+        MW_LAUNCH_CHECK();
+    }
     if (!o->device_ptrs && !o->host_async) MW_CUDA(cudaStreamSynchronize(o->stream));
     o->have_h0 = true;
     return MW_OK;
@@ -369,12 +391,12 @@ extern "C" int mw_ocean_get_rest_vertices(mw_ocean* o, float* xyz)
     if (!o || !xyz) { mw_set_error("null argument"); return MW_E_INVALID_ARG; }
     const int N = o->N;
     const float uw = o->p.unit_width;
-    // FFTMesh.cs:104-112 (resolution is even here)
+    // FFTMesh.cs:104-112: the half-cell offset applies to even resolutions only
     for (int i = 0; i < N; ++i) {
         volatile float hp = (float)(i - N / 2) * uw;
         for (int j = 0; j < N; ++j) {
             volatile float vp = (float)(j - N / 2) * uw;
-            volatile float off = uw / 2.0f;
+            volatile float off = (N % 2 == 0) ? uw / 2.0f : 0.0f;
             float* v = xyz + 3 * ((size_t)i * N + j);
             v[0] = hp + off; v[1] = 0.f; v[2] = vp + off;
         }
@@ -599,6 +621,24 @@ extern "C" int mw_ocean_generate(mw_ocean* o, float t, const mw_ocean_out* out)
 
     // host-pointer mode: the scratch outputs of the previous frame may still be on their way to the host
     if (!dev && o->copies_pending) MW_CUDA(cudaStreamWaitEvent(o->stream, o->ev_copied, 0));
+    if (o->direct) {
+        // the whitecap needs hds and the normal whatever the caller asked for
+        if ((d_white || d_jac) && !d_disp) { if ((rc = ensure(&o->s_disp, total))) return rc; d_disp = o->s_disp; }
+        if (d_white && !d_normal) { if ((rc = ensure(&o->s_normal, total * 3))) return rc; d_normal = o->s_normal; }
+        mwk::k_direct_htilde<<<(unsigned)((total + 255) / 256), 256, 0, o->stream>>>(o->spec, o->omega, o->dH, (int64_t)o->n2, o->tiles, t);
+        MW_LAUNCH_CHECK();
+        {
+            ProfScope ps(o, 0);
+            mwk::k_direct_displace<<<dim3((unsigned)o->n2, (unsigned)o->tiles), mwk::DIRECT_THREADS, 0, o->stream>>>(
+                o->dH, d_height, d_disp, d_normal, o->N, o->p.unit_width, o->p.length);
+            MW_LAUNCH_CHECK();
+        }
+        if (d_white || d_jac) {
+            ProfScope ps(o, 1);
+            mwk::k_direct_whitecap<<<(unsigned)((total + 255) / 256), 256, 0, o->stream>>>(d_disp, d_normal, d_white, d_jac, o->N, o->tiles);
+            MW_LAUNCH_CHECK();
+        }
+    } else {
     // e^{i omega t} for every distinct omega of the grid (one entry per multiple of w0), then the frame
     mwk::k_phase_table<<<(unsigned)((o->q_entries + 255) / 256), 256, 0, o->stream>>>(o->ptab, o->q_entries, o->p.length, t);
     MW_LAUNCH_CHECK();
@@ -611,6 +651,7 @@ extern "C" int mw_ocean_generate(mw_ocean* o, float t, const mw_ocean_out* out)
             (rc = encode_plane(&ca.tm_normal, d_normal, o->N, o->tiles, 3))) return rc;
     }
     if ((rc = run_frame(o, ra, ca))) return rc;
+    }
 
     float* d_vert = nullptr; float4* d_col = nullptr;
     if (mesh) {

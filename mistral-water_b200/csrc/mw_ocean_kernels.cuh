@@ -849,8 +849,8 @@ __global__ void k_mesh_outputs(const float* __restrict__ height, const float2* _
     const int idx = (int)(gid % n2);
     const int i = idx / N, j = idx % N;
     if (vertices) {
-        // rest position, FFTMesh.cs:107-112 (N is even): (i - N/2) * uw + uw / 2
-        const float off = __fdiv_rn(unit_width, 2.0f);
+        // rest position, FFTMesh.cs:107-112: (i - N/2) * uw (+ uw / 2 on even grids)
+        const float off = (N % 2 == 0) ? __fdiv_rn(unit_width, 2.0f) : 0.0f;
         const float px = __fadd_rn(__fmul_rn((float)(i - N / 2), unit_width), off);
         const float pz = __fadd_rn(__fmul_rn((float)(j - N / 2), unit_width), off);
         const float2 d = disp[gid];

@@ -46,10 +46,10 @@ def test_struct_layouts_match_header(mw):
 
 
 @pytest.mark.parametrize("kw,frag", [
-    (dict(resolution=100), "power of two"),            # FFT Mesh scene's N=12-style grids: rejected, no O(N^4) path
-    (dict(resolution=16), "power of two"),
+    (dict(resolution=300), "power of two"),            # not a power of two and too large for the direct-sum kernel
+    (dict(resolution=1), "power of two"),
     (dict(resolution=4096), "power of two"),
-    (dict(resolution=64, length=12.39), "periodic"),   # length != resolution * unit_width
+    (dict(resolution=512, length=500.0), "periodic"),  # length != resolution * unit_width above the direct-sum limit
     (dict(resolution=64, unit_width=-1.0, length=-64.0), "positive"),
     (dict(resolution=64, tiles=0), "tiles"),
     (dict(resolution=64, t_division=0.0), "t_division"),
