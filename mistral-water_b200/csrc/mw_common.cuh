@@ -91,6 +91,43 @@ __device__ __forceinline__ float2 ldg_stream2(const float2* p)
     return r;
 }
 
+// Data written by the PREDECESSOR kernel of a programmatic dependent launch (the pass-1 -> pass-2 intermediate, the per-frame
+// phase table, the renderer's images): read after pdl_wait() with plain (weak, coherent) loads.  ld.global.nc promises the
+// data is read-only for the whole lifetime of the reading kernel, which does not hold while the producer grid is still
+// resident next to it -- the non-.nc forms below are what the PTX memory model covers.
+__device__ __forceinline__ float4 ldg_fresh4(const float4* p)
+{
+    float4 r;
+    asm volatile("ld.global.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p) : "memory");
+    return r;
+}
+__device__ __forceinline__ float2 ldg_fresh2(const float2* p)
+{
+    float2 r;
+    asm volatile("ld.global.v2.f32 {%0,%1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p) : "memory");
+    return r;
+}
+__device__ __forceinline__ float4 ld_plain4(const float4* p)
+{
+    float4 r;
+    asm volatile("ld.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p) : "memory");
+    return r;
+}
+__device__ __forceinline__ float ld_plain1(const float* p)
+{
+    float r;
+    asm volatile("ld.global.f32 %0, [%1];" : "=f"(r) : "l"(p) : "memory");
+    return r;
+}
+
+// Developer hooks (phase stamps, "switch one phase off" flags; tools/phase_timing.py): compiled in only with -DMW_DEVHOOKS=1,
+// so that the production kernels carry no trace of them.
+#ifndef MW_DEVHOOKS
+#define MW_DEVHOOKS 0
+#endif
+#define MW_DBG(a, bits) (MW_DEVHOOKS && ((a).dbg_flags & (bits)))
+
 // Streaming variants with an evict-first L2 priority: for data that is touched exactly once (the spectrum on its way in,
 // the outputs on their way out), so that it does not push the pass-1 -> pass-2 intermediate out of the 126 MB L2.
 #ifndef MW_EVICT_FIRST

@@ -74,6 +74,22 @@ struct mw_ocean {
     cudaStream_t aux_stream[3] = {nullptr, nullptr, nullptr};   // streams 1..slots-1 (stream 0 is the caller's)
     cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
     long long* dbg_rows = nullptr; long long* dbg_cols = nullptr;  // developer phase timing (mw_debug_phase_buffers)
+    // CUDA graph of a single-group frame (k_phase_table -> pass 1 -> pass 2 [-> mesh outputs]): what one FFTMesh.Update() costs
+    // is launch latency, not bandwidth -- a 64^2 or 256^2 frame is three back-to-back launches.  Captured the second time the
+    // same output pointers are seen; per frame only the phase table's `t` argument is patched (MW_GRAPH=0 disables).
+    struct FrameGraph {
+        cudaGraph_t graph = nullptr;
+        cudaGraphExec_t exec = nullptr;
+        cudaGraphNode_t phase_node = nullptr;
+        cudaKernelNodeParams phase_params = {};
+        float2* a_ptab = nullptr; int a_entries = 0; float a_length = 0.f, a_t = 0.f;   // argument storage of k_phase_table
+        void* args[4] = {nullptr, nullptr, nullptr, nullptr};
+        void* key[8] = {};
+        void* seen[8] = {};
+        bool have_seen = false;
+        int kernels = 0;
+    } fg;
+    bool graph_enabled = true;
     // profiling
     std::vector<EvPair> ev_pool; size_t ev_used = 0;
     double k_ms[MW_KERNEL_COUNT] = {0, 0, 0};
@@ -212,6 +228,7 @@ extern "C" int mw_ocean_create(const mw_ocean_params* params, mw_ocean** out)
         if (gt > o->tiles) gt = o->tiles;
         o->group_tiles = (int)gt;
         if (const char* e = getenv("MW_PDL")) o->pdl = atoi(e);
+        if (const char* e = getenv("MW_GRAPH")) o->graph_enabled = atoi(e) != 0;
         if (const char* e = getenv("MW_SLOTS")) o->slots = atoi(e);
         if (o->slots < 2) o->slots = 2;
         if (o->slots > 4) o->slots = 4;
@@ -284,6 +301,8 @@ extern "C" void mw_ocean_destroy(mw_ocean* o)
     if (o->ev_computed) cudaEventDestroy(o->ev_computed);
     if (o->ev_copied) cudaEventDestroy(o->ev_copied);
     for (auto& e : o->ev_pool) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+    if (o->fg.exec) cudaGraphExecDestroy(o->fg.exec);
+    if (o->fg.graph) cudaGraphDestroy(o->fg.graph);
     void* ptrs[] = {o->dH, o->s_stage, o->spec, o->spec_r, o->qidx, o->ptab, o->twimg, o->omega, o->ramp, o->kd, o->tw, o->XAB, o->s_height, o->s_disp, o->s_normal,
                     o->s_white, o->s_jac, o->s_vert, o->s_col, o->s_h};
     for (void* q : ptrs) if (q) cudaFree(q);
@@ -318,6 +337,7 @@ extern "C" int mw_ocean_set_stream(mw_ocean* o, void* cuda_stream)
     int rc = drain_events(o);
     if (rc) return rc;
     o->stream = cuda_stream ? (cudaStream_t)cuda_stream : o->own_stream;
+    o->fg.have_seen = false;
     return MW_OK;
 }
 
@@ -638,19 +658,6 @@ extern "C" int mw_ocean_generate(mw_ocean* o, float t, const mw_ocean_out* out)
             mwk::k_direct_whitecap<<<(unsigned)((total + 255) / 256), 256, 0, o->stream>>>(d_disp, d_normal, d_white, d_jac, o->N, o->tiles);
             MW_LAUNCH_CHECK();
         }
-    } else {
-    // e^{i omega t} for every distinct omega of the grid (one entry per multiple of w0), then the frame
-    mwk::k_phase_table<<<(unsigned)((o->q_entries + 255) / 256), 256, 0, o->stream>>>(o->ptab, o->q_entries, o->p.length, t);
-    MW_LAUNCH_CHECK();
-    mwk::RowArgs ra{o->spec_r, o->qidx, o->ptab, o->kd, o->twimg, o->XAB, o->XC, 0, o->dbg_rows, o->dbg_flags, o->pdl};
-    mwk::ColArgs ca{};
-    ca.XAB = o->XAB; ca.XC = o->XC; ca.twimg = o->twimg; ca.height = d_height; ca.disp = d_disp; ca.normal = d_normal;
-    ca.whitecap = d_white; ca.jacobian = d_jac; ca.dbg = o->dbg_cols; ca.dbg_flags = o->dbg_flags; ca.pdl = o->pdl;
-    if (mwk::cols_tma_store(o->N, (d_disp ? 1 : 0) | (d_normal ? 2 : 0) | (d_white ? 4 : 0) | (d_jac ? 8 : 0))) {
-        if ((rc = encode_plane(&ca.tm_white, d_white, o->N, o->tiles, 1)) || (rc = encode_plane(&ca.tm_disp, d_disp, o->N, o->tiles, 2)) ||
-            (rc = encode_plane(&ca.tm_normal, d_normal, o->N, o->tiles, 3))) return rc;
-    }
-    if ((rc = run_frame(o, ra, ca))) return rc;
     }
 
     float* d_vert = nullptr; float4* d_col = nullptr;
@@ -663,10 +670,95 @@ extern "C" int mw_ocean_generate(mw_ocean* o, float t, const mw_ocean_out* out)
             if (dev) d_col = (float4*)out->colors;
             else { if ((rc = ensure(&o->s_col, total))) return rc; d_col = o->s_col; }
         }
-        ProfScope ps(o, 2);
-        mwk::k_mesh_outputs<<<(unsigned)((total + 255) / 256), 256, 0, o->stream>>>(
-            d_height, d_disp, d_white, d_vert, d_col, o->N, o->tiles, o->p.unit_width, o->p.choppiness);
-        MW_LAUNCH_CHECK();
+    }
+    // the kernels of one frame (transform path): phase table, the two passes, the optional mesh-facing epilogue
+    auto issue_frame = [&](float tt) -> int {
+        if (!o->direct) {
+            // e^{i omega t} for every distinct omega of the grid (one entry per multiple of w0), then the frame
+            mwk::k_phase_table<<<(unsigned)((o->q_entries + 255) / 256), 256, 0, o->stream>>>(o->ptab, o->q_entries, o->p.length, tt);
+            MW_LAUNCH_CHECK();
+            mwk::RowArgs ra{o->spec_r, o->qidx, o->ptab, o->kd, o->twimg, o->XAB, o->XC, 0, o->dbg_rows, o->dbg_flags, o->pdl};
+            mwk::ColArgs ca{};
+            ca.XAB = o->XAB; ca.XC = o->XC; ca.twimg = o->twimg; ca.height = d_height; ca.disp = d_disp; ca.normal = d_normal;
+            ca.whitecap = d_white; ca.jacobian = d_jac; ca.dbg = o->dbg_cols; ca.dbg_flags = o->dbg_flags; ca.pdl = o->pdl;
+            if (mwk::cols_tma_store(o->N, (d_disp ? 1 : 0) | (d_normal ? 2 : 0) | (d_white ? 4 : 0) | (d_jac ? 8 : 0))) {
+                int r2;
+                if ((r2 = encode_plane(&ca.tm_white, d_white, o->N, o->tiles, 1)) || (r2 = encode_plane(&ca.tm_disp, d_disp, o->N, o->tiles, 2)) ||
+                    (r2 = encode_plane(&ca.tm_normal, d_normal, o->N, o->tiles, 3))) return r2;
+            }
+            int r3 = run_frame(o, ra, ca);
+            if (r3) return r3;
+        }
+        if (mesh) {
+            ProfScope ps(o, 2);
+            mwk::k_mesh_outputs<<<(unsigned)((total + 255) / 256), 256, 0, o->stream>>>(
+                d_height, d_disp, d_white, d_vert, d_col, o->N, o->tiles, o->p.unit_width, o->p.choppiness);
+            MW_LAUNCH_CHECK();
+        }
+        return MW_OK;
+    };
+    // Single-group frames (one launch per kernel on one stream) are replayed from a CUDA graph: first sighting of a set of
+    // output pointers runs normally (it also sets the kernels' attributes), the second is captured, later ones patch `t`.
+    const bool graphable = o->graph_enabled && !o->direct && !o->profile && o->tiles <= o->group_tiles && !o->dbg_rows && !o->dbg_cols &&
+                           o->dbg_flags == 0;
+    void* key[8] = {d_height, d_disp, d_normal, d_white, d_jac, d_vert, d_col, (void*)o->stream};
+    mw_ocean::FrameGraph& fg = o->fg;
+    if (graphable && fg.exec && memcmp(key, fg.key, sizeof key) == 0) {
+        fg.a_t = t;
+        MW_CUDA(cudaGraphExecKernelNodeSetParams(fg.exec, fg.phase_node, &fg.phase_params));
+        MW_CUDA(cudaGraphLaunch(fg.exec, o->stream));
+        g_mw_launches.fetch_add(fg.kernels, std::memory_order_relaxed);
+    } else if (graphable && fg.have_seen && memcmp(key, fg.seen, sizeof key) == 0) {
+        if (fg.exec) { cudaGraphExecDestroy(fg.exec); fg.exec = nullptr; }
+        if (fg.graph) { cudaGraphDestroy(fg.graph); fg.graph = nullptr; }
+        const long long before = g_mw_launches.load();
+        MW_CUDA(cudaStreamBeginCapture(o->stream, cudaStreamCaptureModeThreadLocal));
+        rc = issue_frame(t);
+        cudaGraph_t g = nullptr;
+        const cudaError_t ce = cudaStreamEndCapture(o->stream, &g);
+        bool ok = rc == MW_OK && ce == cudaSuccess && g != nullptr;
+        if (ok) {
+            // the phase-table node is the only kernel node with k_phase_table as its function
+            size_t nn = 0;
+            ok = cudaGraphGetNodes(g, nullptr, &nn) == cudaSuccess && nn > 0;
+            std::vector<cudaGraphNode_t> nodes(nn);
+            ok = ok && cudaGraphGetNodes(g, nodes.data(), &nn) == cudaSuccess;
+            fg.phase_node = nullptr;
+            for (size_t i = 0; ok && i < nn; ++i) {
+                cudaGraphNodeType ty;
+                if (cudaGraphNodeGetType(nodes[i], &ty) != cudaSuccess || ty != cudaGraphNodeTypeKernel) continue;
+                cudaKernelNodeParams kp = {};
+                if (cudaGraphKernelNodeGetParams(nodes[i], &kp) != cudaSuccess) continue;
+                if (kp.func == (void*)mwk::k_phase_table) { fg.phase_node = nodes[i]; fg.phase_params = kp; }
+            }
+            ok = ok && fg.phase_node != nullptr;
+        }
+        if (ok) {
+            fg.a_ptab = o->ptab; fg.a_entries = o->q_entries; fg.a_length = o->p.length; fg.a_t = t;
+            fg.args[0] = &fg.a_ptab; fg.args[1] = &fg.a_entries; fg.args[2] = &fg.a_length; fg.args[3] = &fg.a_t;
+            fg.phase_params.kernelParams = fg.args;
+            fg.phase_params.extra = nullptr;
+            ok = cudaGraphInstantiate(&fg.exec, g, 0) == cudaSuccess;
+        }
+        if (ok) {
+            fg.graph = g;
+            fg.kernels = (int)(g_mw_launches.load() - before);
+            memcpy(fg.key, key, sizeof key);
+            MW_CUDA(cudaGraphLaunch(fg.exec, o->stream));
+        } else {
+            // capture not possible here (e.g. the caller's stream is already being captured): run the frame the plain way
+            (void)cudaGetLastError();
+            if (g) cudaGraphDestroy(g);
+            if (fg.exec) { cudaGraphExecDestroy(fg.exec); fg.exec = nullptr; }
+            o->graph_enabled = false;
+            g_mw_launches.store(before);
+            if (rc) return rc;
+            if ((rc = issue_frame(t))) return rc;
+        }
+    } else {
+        if ((rc = issue_frame(t))) return rc;
+        memcpy(fg.seen, key, sizeof key);
+        fg.have_seen = graphable;
     }
 
     if (!dev) {
@@ -721,9 +813,11 @@ extern "C" int mw_ocean_kernel_times(mw_ocean* o, float ms[MW_KERNEL_COUNT], int
     return MW_OK;
 }
 
-// Developer hook (not in the public header): device buffers that receive 8 clock64 stamps per CTA.
+// Developer hooks (not in the public header; live only in -DMW_DEVHOOKS=1 builds): device buffers that receive 8 clock64 stamps
+// per CTA, and the "switch one phase off" flags of tools/phase_timing.py.
 extern "C" __attribute__((visibility("default"))) int mw_debug_phase_buffers(mw_ocean* o, long long* rows, long long* cols)
 {
+    if (!MW_DEVHOOKS) { mw_set_error("this library was built without developer hooks (-DMW_DEVHOOKS=1)"); return MW_E_STATE; }
     if (!o) return MW_E_INVALID_ARG;
     o->dbg_rows = rows;
     o->dbg_cols = cols;
@@ -731,6 +825,7 @@ extern "C" __attribute__((visibility("default"))) int mw_debug_phase_buffers(mw_
 }
 extern "C" __attribute__((visibility("default"))) int mw_debug_flags(mw_ocean* o, int flags)
 {
+    if (!MW_DEVHOOKS) { mw_set_error("this library was built without developer hooks (-DMW_DEVHOOKS=1)"); return MW_E_STATE; }
     if (!o) return MW_E_INVALID_ARG;
     o->dbg_flags = flags;
     return MW_OK;

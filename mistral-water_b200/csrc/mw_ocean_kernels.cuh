@@ -250,7 +250,11 @@ __global__ void __launch_bounds__(RP * 3 * (N / fft_pts(N)), MINB) k_spectrum_ro
     const int pair = blockIdx.x * RP + rp;  // < N/2
     float4* lines = all_lines + rp * 3 * LP;
 
+#if MW_DEVHOOKS
 #define MW_RSTAMP(i) do { if (a.dbg && threadIdx.x == 0) a.dbg[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 8 + (i)] = clock64(); } while (0)
+#else
+#define MW_RSTAMP(i) do { } while (0)
+#endif
     MW_RSTAMP(0);
     if (a.pdl == 1) pdl_trigger();
 
@@ -263,8 +267,8 @@ __global__ void __launch_bounds__(RP * 3 * (N / fft_pts(N)), MINB) k_spectrum_ro
     // ---- evolve + pack.  One task = the four grid points (rA|rB, m|m') with m' = -m mod N; the set is
     //      closed under k -> -k, so every Hermitian partner is on hand and every point is read once.
     //      All loads of a thread's (up to) three tasks are issued before the first use. ----
-    if (a.dbg_flags & 512) return;
-    if (!(a.dbg_flags & 32)) {
+    if (MW_DBG(a, 512)) return;
+    if (!MW_DBG(a, 32)) {
         const uint64_t pol = evict_first_policy();
         float4 s1[NIT], s2[NIT], s3[NIT], s4[NIT];
         int q1[NIT], q2[NIT];
@@ -290,8 +294,8 @@ __global__ void __launch_bounds__(RP * 3 * (N / fft_pts(N)), MINB) k_spectrum_ro
         float2 e1[NIT], e2[NIT];
 #pragma unroll
         for (int it = 0; it < NIT; ++it) {
-            e1[it] = __ldg(a.ptab + q1[it]);
-            e2[it] = __ldg(a.ptab + q2[it]);
+            e1[it] = ldg_fresh2(a.ptab + q1[it]);
+            e2[it] = ldg_fresh2(a.ptab + q2[it]);
         }
         // the twiddle tables are fetched while the spectrum loads are in flight
         mwfft::load_twiddle_image<N, RP * PAIR_THREADS, PTS>(smem4, a.twimg);
@@ -389,7 +393,7 @@ __global__ void __launch_bounds__(RP * 3 * (N / fft_pts(N)), MINB) k_spectrum_ro
     // ---- row FFT of the three packed lines ----
     const int q = lt / T, g = lt % T;
     float4* line = lines + q * LP;
-    if (a.dbg_flags & 64) return;
+    if (MW_DBG(a, 64)) return;
     {
         // one instance of the transform for all three lines (code size: the kernel has to stay resident in
         // the instruction cache while several CTAs run different phases); results come back in registers
@@ -563,7 +567,11 @@ __maxnreg__(cols_maxreg(N)) k_cols_extract(const __grid_constant__ ColArgs a)
     float4* line = lines + c * LP;
     auto cta_sync = [] { __syncthreads(); };
 
+#if MW_DEVHOOKS
 #define MW_STAMP(i) do { if (a.dbg && tid == 0) a.dbg[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 8 + (i)] = clock64(); } while (0)
+#else
+#define MW_STAMP(i) do { } while (0)
+#endif
     MW_STAMP(0);
 
     const uint64_t pol = evict_first_policy();  // outputs are written once and not read again by this engine
@@ -575,7 +583,7 @@ __maxnreg__(cols_maxreg(N)) k_cols_extract(const __grid_constant__ ColArgs a)
     // transforms zeros: same instruction stream for every thread, no divergent barrier
     const bool active = is_ab ? (!is_halo || (want_white && b0 + W < N)) : !is_halo;
     if (a.pdl == 1) pdl_trigger();
-    if ((a.dbg_flags & 8) && !is_ab) return;
+    if (MW_DBG(a, 8) && !is_ab) return;
     if (T >= 32 && !active) {  // whole warps with nothing to transform: help with the tables, then leave
         mwfft::load_twiddle_image<N, (W + 1) * T, PTS>(smem4, a.twimg);
         return;                // (exited threads are not waited for by barriers)
@@ -585,17 +593,17 @@ __maxnreg__(cols_maxreg(N)) k_cols_extract(const __grid_constant__ ColArgs a)
     // ---- first-stage inputs straight from global memory: line position p = g + T k holds intermediate row
     //      (p + N/2) mod N = g + T ((k + 8) mod 16)  (the (-1)^a of sigma); slab-major layout => contiguous ----
 #ifndef MW_COLS_TMA
-#define MW_COLS_TMA 0
+#define MW_COLS_TMA 1
 #endif
     __shared__ uint64_t slab_bar;
     if (is_ab && MW_COLS_TMA) {
-        // Build option (-DMW_COLS_TMA=1).  The (A,B) slab is one contiguous block of N * W * 16 bytes (slab-major layout):
-        // ONE thread asks the copy engine for it (cp.async.bulk into the line buffers, which are free until the first stage
-        // writes them), everybody waits on the mbarrier and picks its first-stage inputs out of shared memory.  Measured:
-        // with the intermediate in HBM (one launch for 16 tiles) the load phase shrinks 85 -> 52 us and pass 2 285 -> 267 us
-        // (16 x 576 per-thread loads reach 3.6 TB/s aggregate: the SM's request queue sets the pace, `lg_throttle`); with
-        // the L2-resident intermediate of the default scheduling the extra barrier + shared-memory hop cost more than they
-        // save (frame 426 -> 440 us), hence off by default.
+        // The (A,B) slab is one contiguous block of N * W * 16 bytes (slab-major layout): ONE thread asks the copy engine for
+        // it (cp.async.bulk into the line buffers, which are free until the first stage writes them; SASS: UBLKCP + SYNCS),
+        // everybody waits on the mbarrier and picks its first-stage inputs out of shared memory.  The per-thread alternative
+        // (-DMW_COLS_TMA=0: 16 x 576 LDG.128) keeps only ~24 KB in flight per SM -- the request queue sets the pace
+        // (`lg_throttle`), 3.6 TB/s aggregate against 5.8 TB/s for the bulk copy.  Measured on B200 (profiles/
+        // r02_switch_sweep.jsonl): 16 x 1024^2 frame 406.5 -> 403.6 us with the L2-resident intermediate, 445 -> 437 us with
+        // the intermediate in HBM (one launch for all tiles), 256^2 x 256 301 -> 295 us.
         float4* raw = lines;  // [N][W] float4, aliases the line buffers
         if (tid == 0) mbar_init(&slab_bar, 1);
         __syncthreads();
@@ -609,7 +617,7 @@ __maxnreg__(cols_maxreg(N)) k_cols_extract(const __grid_constant__ ColArgs a)
 #pragma unroll
             for (int k = 0; k < PTS; ++k) {
                 float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (active) e = ldg_stream4(src + (size_t)(T * ((k + PTS / 2) & (PTS - 1))) * W);
+                if (active) e = ldg_fresh4(src + (size_t)(T * ((k + PTS / 2) & (PTS - 1))) * W);
                 v[k].re = make_float2(e.x, e.y);
                 v[k].im = make_float2(e.z, e.w);
             }
@@ -633,7 +641,7 @@ __maxnreg__(cols_maxreg(N)) k_cols_extract(const __grid_constant__ ColArgs a)
 #pragma unroll
         for (int k = 0; k < PTS; ++k) {
             float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (active && !(a.dbg_flags & 4)) e = ldg_stream4(src + (size_t)(T * ((k + PTS / 2) & (PTS - 1))) * W);
+            if (active && !MW_DBG(a, 4)) e = ldg_fresh4(src + (size_t)(T * ((k + PTS / 2) & (PTS - 1))) * W);
             v[k].re = make_float2(e.x, e.y);
             v[k].im = make_float2(e.z, e.w);
         }
@@ -649,8 +657,8 @@ __maxnreg__(cols_maxreg(N)) k_cols_extract(const __grid_constant__ ColArgs a)
             float4 e0 = make_float4(0.f, 0.f, 0.f, 0.f), e1 = e0;
             if (active) {
                 const float4* p = src + (size_t)(T * ((k + PTS / 2) & (PTS - 1))) * (2 * W);
-                e0 = ldg_stream4(p);
-                e1 = ldg_stream4(p + W);
+                e0 = ldg_fresh4(p);
+                e1 = ldg_fresh4(p + W);
             }
             v[k].re = make_float2(e0.x - e0.w, e1.x - e1.w);
             v[k].im = make_float2(e0.y + e0.z, e1.y + e1.z);
@@ -659,7 +667,7 @@ __maxnreg__(cols_maxreg(N)) k_cols_extract(const __grid_constant__ ColArgs a)
     // the twiddle tables are fetched while the slab loads above are in flight
     if (!(is_ab && MW_COLS_TMA)) mwfft::load_twiddle_image<N, (W + 1) * T, PTS>(smem4, a.twimg);
     MW_STAMP(1);
-    if (!(a.dbg_flags & 2)) mwfft::fft_line_inreg<N, +1, PTS>(v, line, g, tw2, tw3, cta_sync);  // one instance for both kinds
+    if (!MW_DBG(a, 2)) mwfft::fft_line_inreg<N, +1, PTS>(v, line, g, tw2, tw3, cta_sync);  // one instance for both kinds
     MW_STAMP(2);
     if (a.pdl == 2) pdl_trigger();
 
@@ -765,8 +773,8 @@ __maxnreg__(cols_maxreg(N)) k_cols_extract(const __grid_constant__ ColArgs a)
         return;
     }
     {
-        const bool own = !is_halo && !(a.dbg_flags & 1);  // halo threads run the same code with every memory access predicated off
-        if (a.dbg_flags & 16) return;
+        const bool own = !is_halo && !MW_DBG(a, 1);  // halo threads run the same code with every memory access predicated off
+        if (MW_DBG(a, 16)) return;
         const int dn = pad_idx(g + 1) - pg;  // padded distance to the next row (1 or 2)
         // east neighbour's line ((small N) halo threads run along with every access predicated off: keep their reads in bounds)
         const float2* De = reinterpret_cast<const float2*>(is_halo ? line : line + LP);
@@ -785,7 +793,7 @@ __maxnreg__(cols_maxreg(N)) k_cols_extract(const __grid_constant__ ColArgs a)
         // column b0 of output row (first row of the warp + rr), as float4 index into the normal plane
         float4* p_nrm = has_normal ? reinterpret_cast<float4*>(a.normal) + (3 * (obase + (size_t)(g - (lane >> LOGW) + rr) * N + b0)) / 4 + qq
                                    : nullptr;
-        const bool nrm_lane = lane < 24 && !(a.dbg_flags & 1) && (T >= 32 || tid - lane + W * rr < W * T);  // (small N: rows of halo lanes do not exist)
+        const bool nrm_lane = lane < 24 && !MW_DBG(a, 1) && (T >= 32 || tid - lane + W * rr < W * T);  // (small N: rows of halo lanes do not exist)
 #pragma unroll
         for (int s0 = 0; s0 < PTS; s0 += NS) {
 #pragma unroll

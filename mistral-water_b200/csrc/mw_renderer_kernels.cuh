@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(slab_w(N) * (N / 16)) k_r_cols(const RColArgs 
         const float4* src = a.XAB + (size_t)xt * xab_tile_elems(N) + ((size_t)blockIdx.x * N + g) * W + c;
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
-            const float4 e = ldg_stream4(src + (size_t)(T * k) * W);
+            const float4 e = ldg_fresh4(src + (size_t)(T * k) * W);
             v[k].re = make_float2(e.x, e.y);
             v[k].im = make_float2(e.z, e.w);
         }
@@ -257,7 +257,7 @@ __global__ void __launch_bounds__(slab_w(N) * (N / 16)) k_r_cols(const RColArgs 
         const float4* src = reinterpret_cast<const float4*>(a.XC + (size_t)xt * plane + ((size_t)(b0 / (2 * W)) * N + g) * (2 * W) + 2 * c);
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
-            const float4 e = ldg_stream4(src + (size_t)(T * k) * W);
+            const float4 e = ldg_fresh4(src + (size_t)(T * k) * W);
             v[k].re = make_float2(e.x, e.z);
             v[k].im = make_float2(e.y, e.w);
         }
@@ -312,11 +312,11 @@ __global__ void __launch_bounds__(256) k_r_maps(const RMapArgs a)
     auto wrap = [&](int i) { return a.repeat ? (i + R) & (R - 1) : min(max(i, 0), R - 1); };
     const int xm = wrap(x - 1), xp = wrap(x + 1), ym = wrap(y - 1), yp = wrap(y + 1);
     const float ts = a.texel_size;
-    const float4 dc = __ldg(D + (size_t)y * R + x);
+    const float4 dc = ld_plain4(D + (size_t)y * R + x);
     // GetVec (OceanNormal.shader:32-37) = (disp.r, height.r, disp.b); center = disp.rgb as written (:44)
     auto vec = [&](int xx, int yy) {
-        const float4 d = __ldg(D + (size_t)yy * R + xx);
-        const float h = __ldg(reinterpret_cast<const float*>(H + (size_t)yy * R + xx));
+        const float4 d = ld_plain4(D + (size_t)yy * R + xx);
+        const float h = ld_plain1(reinterpret_cast<const float*>(H + (size_t)yy * R + xx));
         return make_float3(d.x, h, d.z);
     };
     const float3 vr = vec(xp, y), vl = vec(xm, y), vt = vec(x, ym), vb = vec(x, yp);
@@ -335,8 +335,8 @@ __global__ void __launch_bounds__(256) k_r_maps(const RMapArgs a)
     if (a.white || a.white_rgba || a.jacobian) {
         // WhiteCap.shader:35-36: +-step texel central differences of disp.rb, / 8
         const int st = a.step;
-        const float4 dN = __ldg(D + (size_t)wrap(y - st) * R + x), dS = __ldg(D + (size_t)wrap(y + st) * R + x);
-        const float4 dW = __ldg(D + (size_t)y * R + wrap(x - st)), dE = __ldg(D + (size_t)y * R + wrap(x + st));
+        const float4 dN = ld_plain4(D + (size_t)wrap(y - st) * R + x), dS = ld_plain4(D + (size_t)wrap(y + st) * R + x);
+        const float4 dW = ld_plain4(D + (size_t)y * R + wrap(x - st)), dE = ld_plain4(D + (size_t)y * R + wrap(x + st));
         const float dDdy_x = -0.5f * (dN.x - dS.x) / 8.0f, dDdy_y = -0.5f * (dN.z - dS.z) / 8.0f;
         const float dDdx_x = -0.5f * (dW.x - dE.x) / 8.0f, dDdx_y = -0.5f * (dW.z - dE.z) / 8.0f;
         const float ax = 0.3f * nx, az = 0.3f * nz;                                        // :37
