@@ -181,7 +181,9 @@ def workload_config(args, world, gather_impl="peer"):
         coll = ("one in-place all-gather of the final float buffers per step over NVLink peer memory: every rank's copy engines "
                 "push its slot into the peers' buffers (CUDA IPC mappings), fenced by stream memory operations on peer flag "
                 "words (cuStreamWriteValue32 / cuStreamWaitValue32) -- no kernel, no SM; the ncclAllGather arm is reported under multi_gpu"
-                if gather_impl in ("peer", "p2p") else "one in-place ncclAllGather of the final float buffers per step")
+                if gather_impl in ("peer", "p2p") else
+                "one in-place ncclAllGather of the final float buffers per step (NCCL communicator owned by the tile-set handle); "
+                "the peer-memory arm is reported under multi_gpu")
     return {
         "workload": name,
         "resolution": N, "tiles_per_gpu": T, "points_per_step_per_gpu": T * N * N,
@@ -368,7 +370,7 @@ def run_engine(args):
         st.sync()
         return st, res
 
-    st, main = measure_arm("peer")
+    st, main = measure_arm("auto")     # MW_GATHER_AUTO: peer pushes at 2 GPUs, ncclAllGather above (include/mistral_ocean.h)
     ms, compute_ms, clocks, launches = main["ms"], main["compute_ms"], main["clocks"], main["launches"]
     value = world * pts_rank * K / (ms * 1e-3)
     stream = st.stream
@@ -424,12 +426,12 @@ def run_engine(args):
         roof["kernels"]["note"] = ("serialised on one stream (MW_PROFILE); own_bytes include the 24 B/pt intermediate the kernel "
                                    "itself moves (L2-resident in the timed scheduling) -- sub-figures, not the roofline fraction")
 
-    # ---- the NCCL arm beside the default one (world > 1): same legs, same call counts on every rank ----
-    nccl = None
+    # ---- the other gather arm beside the default one (world > 1): same legs, same call counts on every rank ----
+    other = None
     if world > 1:
         st.close()
         barrier()
-        st2, nccl = measure_arm("nccl")
+        st2, other = measure_arm("nccl" if main["impl"] == "peer" else "peer")
         st2.close()
         barrier()
         st, _ = None, None
@@ -466,7 +468,7 @@ def run_engine(args):
     else:
         # the tile set: every step uploads this rank's h0 from pinned host memory, generates, ALL-GATHERS, and downloads this
         # rank's slot of the gathered buffer once the gather has completed (the hosts fetch each tile once, over N PCIe links)
-        st3 = ShardedTiles(N, rank, world, tiles_per_rank=T, base_seed=1000, device=dev, gather="peer")
+        st3 = ShardedTiles(N, rank, world, tiles_per_rank=T, base_seed=1000, device=dev, gather="auto")
         ts = st3.tileset
         h0, h0c = pin(pts_rank, 2), pin(pts_rank, 2)
         d_h0 = [torch.empty(pts_rank, 2, device=dev) for _ in range(2)]      # upload staging, double-buffered
@@ -568,8 +570,9 @@ def run_engine(args):
                 "ingress_floor_note": f"every rank must RECEIVE (world - 1) x {slot_bytes / 1e6:.1f} MB per step through its NVLink "
                                       f"ingress: {NVLINK_NOMINAL_GBS:.0f} GB/s nominal, {NVLINK_PEER_COPY_GBS:.0f} GB/s measured peer copy",
                 "value_ceiling_at_floor": world * pts_rank / (max(floor_nom, compute_ms / K) * 1e-3),
-                "arms": {"peer": arm(main), "nccl": arm(nccl)},
-                "default_arm": "peer", "rank0_numa_binding": numa,
+                "arms": {main["impl"]: arm(main), other["impl"]: arm(other)},
+                "default_arm": main["impl"], "default_arm_rule": "MW_GATHER_AUTO: peer-memory pushes at 2 GPUs, ncclAllGather above",
+                "rank0_numa_binding": numa,
             }
         emit(line)
     if world > 1:

@@ -87,7 +87,7 @@ namespace MistralWater.Native
         public int world;                  // ranks = GPUs
         public int rank;                   // -1: this process drives every GPU (the Unity host model)
         public int tilesPerRank;
-        public int gather;                 // MW_GATHER_NCCL = 0, MW_GATHER_PEER = 1
+        public int gather;                 // MW_GATHER_NCCL = 0, MW_GATHER_PEER = 1, MW_GATHER_AUTO = 2
         [MarshalAs(UnmanagedType.ByValArray, SizeConst = 16)] public int[] devices;
         public float windStepDeg;          // config 5: 45
         public uint flags;                 // MW_TILES_ASYNC = 1
@@ -153,7 +153,7 @@ namespace MistralWater.Native
 
         // multi-GPU tile sets (no reference counterpart): the handle owns gather buffers, streams, peer mappings and NCCL
         // communicators; rank = -1 drives all GPUs from this one process (ncclCommInitAll / peer copies fenced by events)
-        public const int MW_GATHER_NCCL = 0, MW_GATHER_PEER = 1, MW_TILES_BLOB_BYTES = 512;
+        public const int MW_GATHER_NCCL = 0, MW_GATHER_PEER = 1, MW_GATHER_AUTO = 2, MW_TILES_BLOB_BYTES = 512;
         [DllImport(Lib)] public static extern int mw_tiles_create(ref MwTilesParams p, out IntPtr handle);
         [DllImport(Lib)] public static extern void mw_tiles_destroy(IntPtr handle);
         [DllImport(Lib)] public static extern int mw_tiles_get_layout(IntPtr handle, out MwTilesLayout layout);
@@ -219,12 +219,12 @@ namespace MistralWater.Native
         public readonly IntPtr[] gathered;               // per GPU: [world][slotFloats] floats of the latest frame
 
         public TileSetEngine(int world, int resolution, float unitWidth, float choppiness, float amplitude, Vector2 wind, ulong seed,
-                             bool nccl = false)
+                             int gather = MistralOcean.MW_GATHER_AUTO)
         {
             var p = new MwTilesParams { ocean = new MwOceanParams { resolution = resolution, unitWidth = unitWidth,
                 length = resolution * unitWidth, choppiness = choppiness, amplitude = amplitude, windX = wind.x, windY = wind.y,
                 tDivision = 1f, seed = seed, tiles = 1 }, world = world, rank = -1, tilesPerRank = 1,
-                gather = nccl ? MistralOcean.MW_GATHER_NCCL : MistralOcean.MW_GATHER_PEER, devices = new int[16], windStepDeg = 45f };
+                gather = gather, devices = new int[16], windStepDeg = 45f };
             for (int i = 0; i < world; ++i) p.devices[i] = i;
             MistralOcean.Check(MistralOcean.mw_tiles_create(ref p, out handle));
             MistralOcean.Check(MistralOcean.mw_tiles_get_layout(handle, out layout));

@@ -334,7 +334,14 @@ int mw_wave_displace(const mw_wave_params* p, const float* pos_xyz, float* out_x
  */
 #define MW_TILES_MAX_WORLD 16
 #define MW_TILES_BLOB_BYTES 512
-enum { MW_GATHER_NCCL = 0, MW_GATHER_PEER = 1 };
+enum {
+    MW_GATHER_NCCL = 0,
+    MW_GATHER_PEER = 1,
+    MW_GATHER_AUTO = 2 /* what measured fastest on 8 x B200 / NVSwitch (profiles/r02_bench_{2,4,8}gpu.json): the peer pushes for
+                          world <= 2 (one flow per link direction: 0.24 vs 0.31 ms per 2048^2 step), ncclAllGather above
+                          (4 GPUs 0.64 vs 0.87 ms, 8 GPUs 1.32 vs 2.20 ms: concurrent copy-engine pushes to several peers reach
+                          only ~370-420 GB/s there, NCCL 570-630 GB/s); peer if NCCL cannot be loaded */
+};
 enum { MW_TILES_ASYNC = 1u << 0 /* generate_allgather only enqueues; mw_tiles_wait / mw_tiles_sync order the results */ };
 
 typedef struct mw_tiles_params {
@@ -343,7 +350,7 @@ typedef struct mw_tiles_params {
     int32_t world;           /* number of ranks = GPUs, 1..MW_TILES_MAX_WORLD                                           */
     int32_t rank;            /* -1: this process drives all ranks; r >= 0: this process is rank r                       */
     int32_t tiles_per_rank;
-    int32_t gather;          /* MW_GATHER_NCCL | MW_GATHER_PEER                                                         */
+    int32_t gather;          /* MW_GATHER_NCCL | MW_GATHER_PEER | MW_GATHER_AUTO                                        */
     int32_t devices[MW_TILES_MAX_WORLD]; /* CUDA ordinal of rank r (rank >= 0: only devices[rank] is read)              */
     float wind_step_deg;     /* config 5: 45                                                                            */
     uint32_t flags;          /* MW_TILES_ASYNC                                                                          */
@@ -388,7 +395,7 @@ int mw_tiles_allgather(mw_tiles* t);
  * errors (ncclCommGetAsyncError) as MW_E_NCCL. */
 int mw_tiles_wait(mw_tiles* t, int frames_back);
 int mw_tiles_sync(mw_tiles* t);
-/* Which implementation runs the gather (MW_GATHER_*), and the text of why a requested one was not available. */
+/* Which implementation runs the gather: MW_GATHER_NCCL or MW_GATHER_PEER (MW_GATHER_AUTO is resolved at create time). */
 int mw_tiles_gather_impl(const mw_tiles* t);
 /* The mw_ocean handle of local rank i (borrowed: owned by the tile set), e.g. for mw_ocean_set_h0 / mw_ocean_kernel_times. */
 mw_ocean* mw_tiles_ocean(mw_tiles* t, int local_rank);

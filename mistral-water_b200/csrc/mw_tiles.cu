@@ -176,6 +176,7 @@ struct mw_tiles {
     int N = 0, world = 1, tpr = 1, nlocal = 1, impl = MW_GATHER_NCCL;
     bool single = true, connected = false, async = false;
     bool kernel_flags = false;   // peer flag writes by k_flag_write instead of cuStreamWriteValue32
+    int push_lanes = 0;          // MW_TILES_PUSH_LANES: 0 = one copy stream per peer; k > 0 = the pushes share k streams
     size_t n2 = 0, slot_floats = 0, alloc_bytes = 0, flags_off = 0;
     std::vector<TileRank> ranks;
     uint32_t frames = 0;     // frames generated so far
@@ -298,6 +299,14 @@ int connect_single(mw_tiles* t)
     return MW_OK;
 }
 
+// the copy stream a push to peer p (the j-th peer visited) goes on
+cudaStream_t push_stream(mw_tiles* t, TileRank& r, int p, int j)
+{
+    if (t->push_lanes <= 0) return r.s_push[p];
+    const int lane = (j - 1) % t->push_lanes;          // j = 1 .. world - 1
+    return r.s_push[(r.rank + 1 + lane) % t->world];   // reuse the streams of the first `lanes` peers
+}
+
 // "flag = value" in stream order, visible system-wide after everything the stream did before
 int flag_write(mw_tiles* t, cudaStream_t s, uint32_t* flag, uint32_t value)
 {
@@ -340,9 +349,14 @@ extern "C" int mw_tiles_create(const mw_tiles_params* params, mw_tiles** out)
     if (p.world < 1 || p.world > MAXW) { mw_set_error("world must be in [1, %d], got %d", MAXW, p.world); return MW_E_INVALID_ARG; }
     if (p.rank < -1 || p.rank >= p.world) { mw_set_error("rank %d out of range for world %d", p.rank, p.world); return MW_E_INVALID_ARG; }
     if (p.tiles_per_rank < 1) { mw_set_error("tiles_per_rank must be >= 1"); return MW_E_INVALID_ARG; }
-    if (p.gather != MW_GATHER_NCCL && p.gather != MW_GATHER_PEER) { mw_set_error("gather must be MW_GATHER_NCCL or MW_GATHER_PEER"); return MW_E_INVALID_ARG; }
-    if (p.gather == MW_GATHER_NCCL && p.world > 1 && !nccl_api()->ok) { mw_set_error("MW_GATHER_NCCL: %s", nccl_api()->why); return MW_E_NCCL; }
-    if (p.gather == MW_GATHER_PEER && p.rank >= 0 && p.world > 1 && !memops()->ok) {
+    if (p.gather != MW_GATHER_NCCL && p.gather != MW_GATHER_PEER && p.gather != MW_GATHER_AUTO) {
+        mw_set_error("gather must be MW_GATHER_NCCL, MW_GATHER_PEER or MW_GATHER_AUTO");
+        return MW_E_INVALID_ARG;
+    }
+    // MW_GATHER_AUTO: see include/mistral_ocean.h -- every rank of a node resolves it the same way
+    const int gather = p.gather != MW_GATHER_AUTO ? p.gather : ((p.world <= 2 || !nccl_api()->ok) ? MW_GATHER_PEER : MW_GATHER_NCCL);
+    if (gather == MW_GATHER_NCCL && p.world > 1 && !nccl_api()->ok) { mw_set_error("MW_GATHER_NCCL: %s", nccl_api()->why); return MW_E_NCCL; }
+    if (gather == MW_GATHER_PEER && p.rank >= 0 && p.world > 1 && !memops()->ok) {
         mw_set_error("MW_GATHER_PEER between processes needs cuStreamWriteValue32 / cuStreamWaitValue32");
         return MW_E_CUDA;
     }
@@ -354,8 +368,9 @@ extern "C" int mw_tiles_create(const mw_tiles_params* params, mw_tiles** out)
     t->tpr = p.tiles_per_rank;
     t->single = p.rank < 0;
     t->nlocal = t->single ? p.world : 1;
-    t->impl = p.gather;
+    t->impl = gather;
     t->async = (p.flags & MW_TILES_ASYNC) != 0;
+    if (const char* e = getenv("MW_TILES_PUSH_LANES")) t->push_lanes = atoi(e);
     t->n2 = (size_t)t->N * t->N;
     t->slot_floats = (size_t)t->tpr * t->n2 * 7;
     t->flags_off = ((size_t)2 * t->world * t->slot_floats * sizeof(float) + 255) & ~(size_t)255;
@@ -598,7 +613,7 @@ int enqueue_gather(mw_tiles* t, int b)
             for (int j = 1; j < t->world; ++j) {
                 const int p = (r.rank + j) % t->world;
                 TileRank& dst = t->ranks[p];
-                cudaStream_t s = r.s_push[p];
+                cudaStream_t s = push_stream(t, r, p, j);
                 if (r.gen_used[b]) MW_CUDA(cudaStreamWaitEvent(s, r.ev_gen[b], 0));
                 MW_CUDA(cudaStreamWaitEvent(s, dst.ev_free[b], 0));
                 MW_CUDA(cudaMemcpyPeerAsync(dst.gather[b] + (size_t)r.rank * t->slot_floats, dst.device, src, r.device, slot_bytes, s));
@@ -629,7 +644,7 @@ int enqueue_gather(mw_tiles* t, int b)
         const float* src = r.gather[b] + (size_t)r.rank * t->slot_floats;
         for (int j = 1; j < t->world; ++j) {
             const int p = (r.rank + j) % t->world;
-            cudaStream_t s = r.s_push[p];
+            cudaStream_t s = push_stream(t, r, p, j);
             if (r.gen_used[b]) MW_CUDA(cudaStreamWaitEvent(s, r.ev_gen[b], 0));
             MW_CU(m->wait32((CUstream)s, (CUdeviceptr)&r.flags->free_[b][p], seq, CU_STREAM_WAIT_VALUE_GEQ));
             MW_CUDA(cudaMemcpyAsync(r.peer_gather[b][p] + (size_t)r.rank * t->slot_floats, src, slot_bytes, cudaMemcpyDeviceToDevice, s));

@@ -41,7 +41,7 @@ EXPORTS = (
 )
 MW_TILES_MAX_WORLD = 16
 MW_TILES_BLOB_BYTES = 512
-MW_GATHER_NCCL, MW_GATHER_PEER = 0, 1
+MW_GATHER_NCCL, MW_GATHER_PEER, MW_GATHER_AUTO = 0, 1, 2
 MW_TILES_ASYNC = 1 << 0
 
 

@@ -80,7 +80,7 @@ class TileSet:
     """
 
     def __init__(self, N: int, world: int, rank: int | None = None, devices=None, tiles_per_rank: int = 1,
-                 gather: str = "peer", base_seed: int = 1000, wind=(5.0, 3.0), amplitude: float = 0.01,
+                 gather: str = "auto", base_seed: int = 1000, wind=(5.0, 3.0), amplitude: float = 0.01,
                  unit_width: float = 1.0, choppiness: float = 1.0, wind_step_deg: float = 45.0, asynchronous: bool = True,
                  profile: bool = False, exchange=None):
         import ctypes as C
@@ -98,7 +98,8 @@ class TileSet:
         p.ocean = native.OceanParams(int(N), float(unit_width), length, float(choppiness), float(amplitude), float(wind[0]),
                                      float(wind[1]), 1.0, int(base_seed), 0, 1, native.MW_PROFILE if profile else 0, 0)
         p.world, p.rank, p.tiles_per_rank = self.world, (-1 if rank is None else int(rank)), self.tiles_per_rank
-        p.gather = {"nccl": native.MW_GATHER_NCCL, "peer": native.MW_GATHER_PEER, "p2p": native.MW_GATHER_PEER}[gather]
+        p.gather = {"nccl": native.MW_GATHER_NCCL, "peer": native.MW_GATHER_PEER, "p2p": native.MW_GATHER_PEER,
+                    "auto": native.MW_GATHER_AUTO}[gather]
         for i, d in enumerate(devices[:native.MW_TILES_MAX_WORLD]):
             p.devices[i] = int(d)
         p.wind_step_deg = float(wind_step_deg)
@@ -233,7 +234,7 @@ class ShardedTiles:
         devices = [0] * world
         devices[rank] = dev_index
         self.tileset = TileSet(N, world, rank=rank, devices=devices, tiles_per_rank=tiles_per_rank,
-                               gather=gather or os.environ.get("MW_GATHER", "peer"), base_seed=base_seed, wind=wind,
+                               gather=gather or os.environ.get("MW_GATHER", "auto"), base_seed=base_seed, wind=wind,
                                amplitude=amplitude, unit_width=unit_width, choppiness=choppiness, asynchronous=True,
                                profile=profile, exchange=exchange if world > 1 else None)
         self.gather_impl = self.tileset.gather_impl
