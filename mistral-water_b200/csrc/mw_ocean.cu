@@ -90,6 +90,9 @@ struct mw_ocean {
         int kernels = 0;
     } fg;
     bool graph_enabled = true;
+    // small single frames (N <= 256, at most 2^18 grid points per call): pass 1 evaluates e^{i omega t} itself and the
+    // k_phase_table launch disappears -- such a frame is a chain of launch latencies (MW_INLINE_PHASE=0 disables)
+    bool inline_phase = false;
     // profiling
     std::vector<EvPair> ev_pool; size_t ev_used = 0;
     double k_ms[MW_KERNEL_COUNT] = {0, 0, 0};
@@ -229,6 +232,8 @@ extern "C" int mw_ocean_create(const mw_ocean_params* params, mw_ocean** out)
         o->group_tiles = (int)gt;
         if (const char* e = getenv("MW_PDL")) o->pdl = atoi(e);
         if (const char* e = getenv("MW_GRAPH")) o->graph_enabled = atoi(e) != 0;
+        o->inline_phase = o->N <= 256 && o->n2 * (size_t)o->tiles <= ((size_t)1 << 18);
+        if (const char* e = getenv("MW_INLINE_PHASE")) o->inline_phase = o->inline_phase && atoi(e) != 0;
         if (const char* e = getenv("MW_SLOTS")) o->slots = atoi(e);
         if (o->slots < 2) o->slots = 2;
         if (o->slots > 4) o->slots = 4;
@@ -453,24 +458,32 @@ extern "C" int mw_ocean_evolve_spectrum(mw_ocean* o, float t, float* htilde)
 // ---------------------------------------------------------------------------------------------
 // per-frame launches
 // ---------------------------------------------------------------------------------------------
-template <int N, int RP, int MINB>
-static int launch_rows(mw_ocean* o, const mwk::RowArgs& a, int ntiles, cudaStream_t st)
+template <int N, int RP, int MINB, bool INLINE_PHASE>
+static int launch_rows_impl(mw_ocean* o, const mwk::RowArgs& a, int ntiles, cudaStream_t st)
 {
     constexpr int PTS = mwk::fft_pts(N);
     constexpr int threads = RP * 3 * (N / PTS);
     constexpr size_t smem = mwfft::Plan<N, PTS>::TW_BYTES + (size_t)RP * 3 * mwfft::line_pitch(N, 8) * sizeof(float4);
     static bool attr_done[64] = {};
     if (!attr_done[o->p.device]) {
-        MW_CUDA(cudaFuncSetAttribute(mwk::k_spectrum_rows<N, RP, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        MW_CUDA(cudaFuncSetAttribute(mwk::k_spectrum_rows<N, RP, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout,
+        MW_CUDA(cudaFuncSetAttribute(mwk::k_spectrum_rows<N, RP, MINB, INLINE_PHASE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        MW_CUDA(cudaFuncSetAttribute(mwk::k_spectrum_rows<N, RP, MINB, INLINE_PHASE>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                      cudaSharedmemCarveoutMaxShared));
         attr_done[o->p.device] = true;
     }
     dim3 grid(N / 2 / RP, ntiles);
     ProfScope ps(o, 0);
-    MW_CUDA(mw_launch(mwk::k_spectrum_rows<N, RP, MINB>, grid, threads, smem, st, o->pdl != 0, a));
+    MW_CUDA(mw_launch(mwk::k_spectrum_rows<N, RP, MINB, INLINE_PHASE>, grid, threads, smem, st, o->pdl != 0, a));
     MW_LAUNCH_CHECK();
     return MW_OK;
+}
+template <int N, int RP, int MINB>
+static int launch_rows(mw_ocean* o, const mwk::RowArgs& a, int ntiles, cudaStream_t st)
+{
+    if constexpr (N <= 256) {
+        if (o->inline_phase) return launch_rows_impl<N, RP, MINB, true>(o, a, ntiles, st);
+    }
+    return launch_rows_impl<N, RP, MINB, false>(o, a, ntiles, st);
 }
 
 template <int N, int MINB, int OUTS>
@@ -675,9 +688,12 @@ extern "C" int mw_ocean_generate(mw_ocean* o, float t, const mw_ocean_out* out)
     auto issue_frame = [&](float tt) -> int {
         if (!o->direct) {
             // e^{i omega t} for every distinct omega of the grid (one entry per multiple of w0), then the frame
-            mwk::k_phase_table<<<(unsigned)((o->q_entries + 255) / 256), 256, 0, o->stream>>>(o->ptab, o->q_entries, o->p.length, tt);
-            MW_LAUNCH_CHECK();
-            mwk::RowArgs ra{o->spec_r, o->qidx, o->ptab, o->kd, o->twimg, o->XAB, o->XC, 0, o->dbg_rows, o->dbg_flags, o->pdl};
+            if (!o->inline_phase) {
+                mwk::k_phase_table<<<(unsigned)((o->q_entries + 255) / 256), 256, 0, o->stream>>>(o->ptab, o->q_entries, o->p.length, tt);
+                MW_LAUNCH_CHECK();
+            }
+            mwk::RowArgs ra{o->spec_r, o->qidx, o->ptab, o->kd, o->twimg, o->XAB, o->XC, 0, o->dbg_rows, o->dbg_flags, o->pdl,
+                            o->p.length, tt};
             mwk::ColArgs ca{};
             ca.XAB = o->XAB; ca.XC = o->XC; ca.twimg = o->twimg; ca.height = d_height; ca.disp = d_disp; ca.normal = d_normal;
             ca.whitecap = d_white; ca.jacobian = d_jac; ca.dbg = o->dbg_cols; ca.dbg_flags = o->dbg_flags; ca.pdl = o->pdl;
@@ -699,7 +715,7 @@ extern "C" int mw_ocean_generate(mw_ocean* o, float t, const mw_ocean_out* out)
     };
     // Single-group frames (one launch per kernel on one stream) are replayed from a CUDA graph: first sighting of a set of
     // output pointers runs normally (it also sets the kernels' attributes), the second is captured, later ones patch `t`.
-    const bool graphable = o->graph_enabled && !o->direct && !o->profile && o->tiles <= o->group_tiles && !o->dbg_rows && !o->dbg_cols &&
+    const bool graphable = o->graph_enabled && !o->inline_phase && !o->direct && !o->profile && o->tiles <= o->group_tiles && !o->dbg_rows && !o->dbg_cols &&
                            o->dbg_flags == 0;
     void* key[8] = {d_height, d_disp, d_normal, d_white, d_jac, d_vert, d_col, (void*)o->stream};
     mw_ocean::FrameGraph& fg = o->fg;

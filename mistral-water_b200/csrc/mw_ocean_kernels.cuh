@@ -203,6 +203,7 @@ struct RowArgs {
     long long* dbg;        // developer phase-timing buffer (NULL in production)
     int dbg_flags;         // developer experiments: 1 = no output stores, 2 = no FFT, 4 = no spectrum loads
     int pdl;               // programmatic dependent launch: 1 = release the successor at CTA start, 2 = before the result stores
+    float length, t;       // INLINE_PHASE kernels only: e^{i omega t} is evaluated here instead of being read from ptab
 };
 
 // Signs.  The direct sum equals sigma[a,b] * T[a,b] with sigma = -(-1)^(a+b), and Dz carries an
@@ -229,7 +230,10 @@ __device__ __forceinline__ float2 htilde_tab(float4 s, float2 e)
 }
 
 // RP row pairs per CTA; 3 packed lines per pair: (A,B) of row rA, (A,B) of row rB, (C of rA, C of rB).
-template <int N, int RP, int MINB>
+// INLINE_PHASE (small single frames, where a frame is a chain of launch latencies): the two e^{i omega t} of a task are
+// evaluated here -- sincosf(fl(fl(q w0) t)), the very expression k_phase_table tabulates, hence bit-identical -- so that the
+// frame is two kernels instead of three.
+template <int N, int RP, int MINB, bool INLINE_PHASE = false>
 __global__ void __launch_bounds__(RP * 3 * (N / fft_pts(N)), MINB) k_spectrum_rows(const RowArgs a)
 {
     constexpr int PTS = fft_pts(N);
@@ -294,8 +298,17 @@ __global__ void __launch_bounds__(RP * 3 * (N / fft_pts(N)), MINB) k_spectrum_ro
         float2 e1[NIT], e2[NIT];
 #pragma unroll
         for (int it = 0; it < NIT; ++it) {
-            e1[it] = ldg_fresh2(a.ptab + q1[it]);
-            e2[it] = ldg_fresh2(a.ptab + q2[it]);
+            if constexpr (INLINE_PHASE) {
+                const float w0 = dispersion_w0(a.length);
+                float sn, cs;
+                sincosf(__fmul_rn(__fmul_rn((float)q1[it], w0), a.t), &sn, &cs);
+                e1[it] = make_float2(cs, sn);
+                sincosf(__fmul_rn(__fmul_rn((float)q2[it], w0), a.t), &sn, &cs);
+                e2[it] = make_float2(cs, sn);
+            } else {
+                e1[it] = ldg_fresh2(a.ptab + q1[it]);
+                e2[it] = ldg_fresh2(a.ptab + q2[it]);
+            }
         }
         // the twiddle tables are fetched while the spectrum loads are in flight
         mwfft::load_twiddle_image<N, RP * PAIR_THREADS, PTS>(smem4, a.twimg);

@@ -391,7 +391,28 @@ def test_graph_replay_equals_plain_launches(mw, N, monkeypatch):
 
     plain, n_plain = run(False)
     graph, n_graph = run(True)
-    assert n_plain == n_graph == 3 * len(times)          # the launch counter counts the kernels a replayed graph runs
+    # the launch counter counts the kernels a replayed graph runs; small single frames (N <= 256) evaluate the phases inside
+    # pass 1 and are two kernels, not three (and are not graphed)
+    assert n_plain == n_graph == (2 if N <= 256 else 3) * len(times)
     for a, b in zip(plain, graph):
         for k in names:
             assert torch.equal(a[k], b[k]), k
+
+
+@pytest.mark.parametrize("N,tiles", [(32, 1), (64, 1), (256, 1), (256, 4), (128, 16)])
+def test_inline_phase_frames_equal_table_frames(mw, N, tiles, monkeypatch):
+    """Small single frames skip k_phase_table: pass 1 evaluates sincosf(fl(fl(q w0) t)) itself -- the expression the table
+    holds -- so the outputs are bit-identical to the three-kernel frame (MW_INLINE_PHASE=0), at large t too."""
+    outs = []
+    for inline in ("1", "0"):
+        monkeypatch.setenv("MW_INLINE_PHASE", inline)
+        with mw.Ocean(N, seed=9, tiles=tiles) as o:
+            o.init_spectrum()
+            before = mw.native.launch_count()
+            res = [o.generate(t) for t in (0.0, 1.7, 3600.0)]
+            per_frame = (mw.native.launch_count() - before) // 3
+            assert per_frame == (2 if inline == "1" else 3)
+            outs.append(res)
+    for a, b in zip(*outs):
+        for k in a:
+            assert np.array_equal(a[k], b[k]), k
