@@ -17,7 +17,8 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
         "l1tex__throughput.avg.pct_of_peak_sustained_active", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
-        "sm__inst_executed.avg.per_cycle_elapsed"]
+        "sm__inst_executed.avg.per_cycle_elapsed", "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active", "sm__cycles_elapsed.max"]
 
 
 def raw(rep):
@@ -42,8 +43,10 @@ md = [f"# profiles/{R}: ncu summaries (B200, sm_100a)\n",
       "Source reports: `gpurun_out/" + R + "_*.ncu-rep` (scratch, not tracked). Commands: `tools/profile_round.sh`.",
       "Durations under ncu are cold-cache and serialised; use them for shares and traffic, not for throughput.\n"]
 traffic = {}
-for tag, title in (("frame_grouped", "frame kernels, default scheduling (1 tile of 1024^2 per launch)"),
-                   ("frame_batched", "frame kernels, one launch for all 16 tiles (MW_GROUP_TILES=16)"),
+for tag, title in (("frame_grouped", "frame kernels, default scheduling (1 tile of 1024^2 per launch, --cache-control none: intermediate L2-resident as in the timed region)"),
+                   ("frame_batched", "frame kernels, one launch for all 16 tiles (MW_GROUP_TILES=16: steady state over many waves, intermediate through HBM)"),
+                   ("frame_2048", "frame kernels, one 2048^2 tile (BASELINE configs[4] per-rank work)"),
+                   ("frame_256", "frame kernels, 256 x 256^2 in one launch (MW_GROUP_TILES=256)"),
                    ("gerstner", "k_gerstner, 32 waves x 1048576 vertices"),
                    ("renderer", "OceanRenderer path, 16 x (1024^2 maps) per call: k_r_rows, k_r_cols, k_r_maps")):
     rep = os.path.join(G, f"{R}_{tag}.ncu-rep")
@@ -60,7 +63,7 @@ for tag, title in (("frame_grouped", "frame kernels, default scheduling (1 tile 
                 md.append(f"| {k} | {d[k]} | {units.get(k, '')} |")
         md.append("")
         md.append("top warp-stall reasons (warps per issue-active cycle): " + ", ".join(f"{k} {v:.2f}" for k, v in stalls(d)) + "\n")
-        if tag == "frame_batched":
+        if False and tag == "frame_batched":
             def tobytes(x, u):
                 return float(x) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
             short = "k_cols_extract" if "cols_extract" in name else "k_spectrum_rows"
@@ -82,7 +85,7 @@ if os.path.exists(lc):
         a[0] += 1
         a[1] += val_us
     tot = sum(v[1] for v in agg.values())
-    md.append(f"## launch list of `python bench.py --steps 2 --warmup 3 --no-cpu-baseline --e2e-steps 1` ({len(rows)} launches)\n")
+    md.append(f"## launch list of `python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extra-configs --e2e-steps 1` ({len(rows)} launches)\n")
     md.append("| kernel | launches | total us | share |\n|---|---|---|---|")
     for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         md.append(f"| `{k[:90]}` | {v[0]} | {v[1]:.1f} | {100 * v[1] / tot:.1f}% |")
@@ -97,7 +100,16 @@ for fn in (f"{R}_bench.json", f"{R}_extra.json", f"{R}_smi.csv"):
     src = os.path.join(G, fn)
     if os.path.exists(src):
         open(os.path.join(P, fn), "w").write(open(src).read())
+# DRAM traffic of one whole frame in the timed scheduling (tools/traffic_frame.py under ncu --replay-mode application)
+for tag in ("traffic_grouped", "traffic_batched"):
+    src = os.path.join(G, f"{R}_{tag}.json")
+    if os.path.exists(src):
+        t = json.load(open(src))
+        open(os.path.join(P, f"{R}_{tag}.json"), "w").write(open(src).read())
+        md.append(f"## DRAM traffic of one 16 x 1024^2 frame, `{tag}` (ncu --replay-mode application --cache-control none, summed over the frame's launches)\n")
+        md.append("| kernel | launches | dram read MB | dram write MB | serialised us |\n|---|---|---|---|---|")
+        for k, v in t["kernels"].items():
+            md.append(f"| `{k}` | {v['launches']} | {v['dram_read'] / 1e6:.1f} | {v['dram_write'] / 1e6:.1f} | {v['time_us']:.1f} |")
+        md.append(f"\ntotal {t['total_bytes'] / 1e6:.1f} MB per frame against 738.2 MB algorithmic (44 B x 16 777 216 points): x{t['total_bytes'] / 738197504:.2f}\n")
 open(os.path.join(P, f"{R}_summary.md"), "w").write("\n".join(md) + "\n")
-json.dump(traffic, open(os.path.join(P, "traffic.json"), "w"), indent=1)
-print("\n".join(md)[:6000])
-print(traffic)
+print("\n".join(md)[:3000])
