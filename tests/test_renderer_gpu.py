@@ -133,6 +133,26 @@ def test_ocean_demo_scene_component_lifecycle(mw, ror):
     c.close()
 
 
+def test_default_resolution_2048_maps_against_the_fp64_form(mw, ror):
+    """R = 2048 (OceanRenderer's default resolution 256, OceanRenderer.cs:13) against the oracle itself, not only properties:
+    two frames of all four maps vs the fp64 evaluation of the shader chain on the same initial spectrum (~30 s of numpy)."""
+    res = 256
+    with _engine(mw, res) as r:
+        r.render_initial()
+        ini = r.get_initial()
+        s = _state(ror, res, F64, initial=ini[0])
+        for _ in range(2):
+            got = r.generate_texture(0.02)
+            want = s.generate_texture(0.02)
+        assert max_abs(r.get_phase()[0], want["phase"]) <= 3e-6
+    for k in ("displacement", "height"):
+        assert rel_l2(got[k][0], want[k]) <= 1e-5, (k, rel_l2(got[k][0], want[k]))
+    # OceanNormal's stencil normalises cross products of DIFFERENCES of displaced positions one texel apart: its conditioning
+    # grows as the texel shrinks (434.48 / 2048 = 0.21 here against 0.42 at R = 1024, where 5e-6 is measured): 1.13e-5 measured
+    assert rel_l2(got["normal"][0], want["normal"]) <= 2.5e-5, rel_l2(got["normal"][0], want["normal"])
+    _check_white(got["white"][0, ..., 0], want["white"])
+
+
 def test_full_size_properties_2048(mw):
     """R = 2048 (the default resolution 256, OceanRenderer.cs:13): properties that need no oracle run.
     Linearity of the whole spectral chain in the initial spectrum; phase accumulation; unit normals."""
