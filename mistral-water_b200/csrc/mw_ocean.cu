@@ -7,6 +7,7 @@
 
 #include "mw_ocean_kernels.cuh"
 #include "mw_direct_kernels.cuh"
+#include "mw_cols_seam.cuh"
 
 // ---------------------------------------------------------------------------------------------
 // error text (thread-local) and global launch counter
@@ -24,6 +25,10 @@ void mw_set_error(const char* fmt, ...)
 extern "C" const char* mw_last_error(void) { return t_err; }
 extern "C" int mw_version(void) { return MW_VERSION; }
 extern "C" int64_t mw_kernel_launch_count(void) { return (int64_t)g_mw_launches.load(); }
+
+#ifndef MW_SEAM_DEFAULT
+#define MW_SEAM_DEFAULT 1
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // handle
@@ -93,6 +98,10 @@ struct mw_ocean {
     // small single frames (N <= 256, at most 2^18 grid points per call): pass 1 evaluates e^{i omega t} itself and the
     // k_phase_table launch disappears -- such a frame is a chain of launch latencies (MW_INLINE_PHASE=0 disables)
     bool inline_phase = false;
+    // pass 2 without the halo line (mw_cols_seam.cuh): the east neighbour's column is handed over by the CTA that owns it
+    bool use_seam = false;
+    float2* seam = nullptr;          // [tiles][N / W][N]
+    unsigned* seam_flags = nullptr;  // [tiles][N / W]
     // profiling
     std::vector<EvPair> ev_pool; size_t ev_used = 0;
     double k_ms[MW_KERNEL_COUNT] = {0, 0, 0};
@@ -234,6 +243,17 @@ extern "C" int mw_ocean_create(const mw_ocean_params* params, mw_ocean** out)
         if (const char* e = getenv("MW_GRAPH")) o->graph_enabled = atoi(e) != 0;
         o->inline_phase = o->N <= 256 && o->n2 * (size_t)o->tiles <= ((size_t)1 << 18);
         if (const char* e = getenv("MW_INLINE_PHASE")) o->inline_phase = o->inline_phase && atoi(e) != 0;
+        // pass 2 without the halo line: measured faster from N = 512 up (profiles/r02_seam_sweep.jsonl: 16 x 1024^2 402 -> 383 us,
+        // 64 x 512^2 394 -> 342 us, 4 x 2048^2 536 -> 515 us) and neutral-to-slower below (256^2 x 256 equal, single 64^2 / 128^2
+        // frames + 0.3 - 1 us for the hand-over)
+        o->use_seam = MW_SEAM_DEFAULT != 0 && N >= 512;
+        if (const char* e = getenv("MW_SEAM")) o->use_seam = atoi(e) != 0;
+        if (o->use_seam) {
+            const size_t nab = (size_t)(N / mwk::slab_w(N));
+            if ((rc = ensure(&o->seam, (size_t)o->tiles * nab * N))) return fail(rc);
+            if ((rc = ensure(&o->seam_flags, (size_t)o->tiles * nab + 1))) return fail(rc);   // + the time-out counter
+            if (cudaMemset(o->seam_flags, 0, ((size_t)o->tiles * nab + 1) * sizeof(unsigned)) != cudaSuccess) { mw_set_error("cudaMemset failed"); return fail(MW_E_CUDA); }
+        }
         if (const char* e = getenv("MW_SLOTS")) o->slots = atoi(e);
         if (o->slots < 2) o->slots = 2;
         if (o->slots > 4) o->slots = 4;
@@ -308,7 +328,7 @@ extern "C" void mw_ocean_destroy(mw_ocean* o)
     for (auto& e : o->ev_pool) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     if (o->fg.exec) cudaGraphExecDestroy(o->fg.exec);
     if (o->fg.graph) cudaGraphDestroy(o->fg.graph);
-    void* ptrs[] = {o->dH, o->s_stage, o->spec, o->spec_r, o->qidx, o->ptab, o->twimg, o->omega, o->ramp, o->kd, o->tw, o->XAB, o->s_height, o->s_disp, o->s_normal,
+    void* ptrs[] = {o->seam, o->seam_flags, o->dH, o->s_stage, o->spec, o->spec_r, o->qidx, o->ptab, o->twimg, o->omega, o->ramp, o->kd, o->tw, o->XAB, o->s_height, o->s_disp, o->s_normal,
                     o->s_white, o->s_jac, o->s_vert, o->s_col, o->s_h};
     for (void* q : ptrs) if (q) cudaFree(q);
     for (int i = 0; i < 3; ++i) {
@@ -332,6 +352,16 @@ extern "C" int mw_ocean_sync(mw_ocean* o)
     MW_CUDA(cudaStreamSynchronize(o->stream));
     if (o->copy_stream) MW_CUDA(cudaStreamSynchronize(o->copy_stream));
     o->copies_pending = false;
+    if (o->use_seam && o->seam_flags) {
+        // a pass-2 CTA that gave up waiting for its neighbour's column (never expected: mw_cols_seam.cuh) left a wrong whitecap column
+        unsigned n = 0;
+        MW_CUDA(cudaMemcpy(&n, o->seam_flags + (size_t)o->tiles * (o->N / mwk::slab_w(o->N)), sizeof n, cudaMemcpyDeviceToHost));
+        if (n) {
+            cudaMemset(o->seam_flags + (size_t)o->tiles * (o->N / mwk::slab_w(o->N)), 0, sizeof n);
+            mw_set_error("pass 2: %u neighbour-column hand-overs timed out; the whitecap of those slabs' last column is invalid", n);
+            return MW_E_CUDA;
+        }
+    }
     return MW_OK;
 }
 
@@ -487,8 +517,36 @@ static int launch_rows(mw_ocean* o, const mwk::RowArgs& a, int ntiles, cudaStrea
 }
 
 template <int N, int MINB, int OUTS>
+static int launch_cols_seam(mw_ocean* o, mwk::ColArgs a, int ntiles, cudaStream_t st)
+{
+    constexpr int W = mwk::slab_w(N);
+    constexpr int threads = W * (N / mwk::fft_pts(N));
+    constexpr size_t smem = mwk::seam_smem_bytes<N>();
+    static bool attr_done[64] = {};
+    if (!attr_done[o->p.device]) {
+        MW_CUDA(cudaFuncSetAttribute(mwk::k_cols_seam<N, MINB, OUTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        MW_CUDA(cudaFuncSetAttribute(mwk::k_cols_seam<N, MINB, OUTS>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                     cudaSharedmemCarveoutMaxShared));
+        attr_done[o->p.device] = true;
+    }
+    const bool want_ab = a.disp || a.normal || a.whitecap || a.jacobian;
+    a.ab_blocks = want_ab ? N / W : 0;
+    const int c_blocks = a.height ? N / (4 * W) : 0;
+    if (a.ab_blocks + c_blocks == 0) return MW_OK;
+    a.seam = o->seam;
+    a.seam_flags = o->seam_flags;
+    a.seam_timeouts = o->seam_flags + (size_t)o->tiles * (N / W);
+    dim3 grid(a.ab_blocks + c_blocks, ntiles);
+    ProfScope ps(o, 1);
+    MW_CUDA(mw_launch(mwk::k_cols_seam<N, MINB, OUTS>, grid, threads, smem, st, o->pdl != 0, a));
+    MW_LAUNCH_CHECK();
+    return MW_OK;
+}
+
+template <int N, int MINB, int OUTS>
 static int launch_cols_outs(mw_ocean* o, mwk::ColArgs a, int ntiles, cudaStream_t st)
 {
+    if (o->use_seam) return launch_cols_seam<N, MINB, OUTS>(o, a, ntiles, st);
     constexpr int W = mwk::slab_w(N);
     constexpr int PTS = mwk::fft_pts(N);
     constexpr int threads = (W + 1) * (N / PTS);
@@ -693,7 +751,7 @@ extern "C" int mw_ocean_generate(mw_ocean* o, float t, const mw_ocean_out* out)
                 MW_LAUNCH_CHECK();
             }
             mwk::RowArgs ra{o->spec_r, o->qidx, o->ptab, o->kd, o->twimg, o->XAB, o->XC, 0, o->dbg_rows, o->dbg_flags, o->pdl,
-                            o->p.length, tt};
+                            o->p.length, tt, o->use_seam ? o->seam_flags : nullptr, o->N / mwk::slab_w(o->N)};
             mwk::ColArgs ca{};
             ca.XAB = o->XAB; ca.XC = o->XC; ca.twimg = o->twimg; ca.height = d_height; ca.disp = d_disp; ca.normal = d_normal;
             ca.whitecap = d_white; ca.jacobian = d_jac; ca.dbg = o->dbg_cols; ca.dbg_flags = o->dbg_flags; ca.pdl = o->pdl;

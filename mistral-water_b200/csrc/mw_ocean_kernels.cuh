@@ -204,6 +204,8 @@ struct RowArgs {
     int dbg_flags;         // developer experiments: 1 = no output stores, 2 = no FFT, 4 = no spectrum loads
     int pdl;               // programmatic dependent launch: 1 = release the successor at CTA start, 2 = before the result stores
     float length, t;       // INLINE_PHASE kernels only: e^{i omega t} is evaluated here instead of being read from ptab
+    unsigned* seam_flags;  // [tiles][seam_nab] "first column published" flags of k_cols_seam (mw_cols_seam.cuh), cleared here; or NULL
+    int seam_nab;
 };
 
 // Signs.  The direct sum equals sigma[a,b] * T[a,b] with sigma = -(-1)^(a+b), and Dz carries an
@@ -295,6 +297,8 @@ __global__ void __launch_bounds__(RP * 3 * (N / fft_pts(N)), MINB) k_spectrum_ro
         // Everything fetched so far is constant across frames.  The phase table is this frame's (k_phase_table), and the
         // intermediate written below may still be being read by the previous pass 2 of this stream: wait for the predecessor.
         pdl_wait();
+        if (a.seam_flags && blockIdx.x == 0)   // (the previous pass 2 of this tile has completed: its flags can go)
+            for (int i = threadIdx.x; i < a.seam_nab; i += RP * PAIR_THREADS) a.seam_flags[(size_t)tile * a.seam_nab + i] = 0u;
         float2 e1[NIT], e2[NIT];
 #pragma unroll
         for (int it = 0; it < NIT; ++it) {
@@ -398,6 +402,8 @@ __global__ void __launch_bounds__(RP * 3 * (N / fft_pts(N)), MINB) k_spectrum_ro
     } else {
         mwfft::load_twiddle_image<N, RP * PAIR_THREADS, PTS>(smem4, a.twimg);
         pdl_wait();
+        if (a.seam_flags && blockIdx.x == 0)
+            for (int i = threadIdx.x; i < a.seam_nab; i += RP * PAIR_THREADS) a.seam_flags[(size_t)tile * a.seam_nab + i] = 0u;
     }
     MW_RSTAMP(1);
     __syncthreads();
@@ -481,6 +487,9 @@ struct ColArgs {
     int pdl;            // programmatic dependent launch: 1 = release the successor at CTA start, 2 = before the extraction
     int ab_blocks;      // blockIdx.x <  ab_blocks : (A,B) slab of 8 columns  (0 if no A/B output is wanted)
                         // blockIdx.x >= ab_blocks : C slab of 32 columns
+    float2* seam;       // k_cols_seam only: [tiles][N / W][N] (dx, dz) / 2 of every slab's first column
+    unsigned* seam_flags;  //               [tiles][N / W] "published" flags (cleared by pass 1)
+    unsigned* seam_timeouts;  //            one counter: hand-overs that gave up waiting (never expected; mw_ocean_sync reports it)
     // TMA descriptors of the whitecap / hds / normal planes as 2-D float tensors [tiles * N rows][N * {1,2,3} floats]
     // (only read by the kernel variants that store through TMA, see cols_tma_store)
     alignas(64) CUtensorMap tm_white, tm_disp, tm_normal;

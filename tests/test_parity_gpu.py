@@ -416,3 +416,25 @@ def test_inline_phase_frames_equal_table_frames(mw, N, tiles, monkeypatch):
     for a, b in zip(*outs):
         for k in a:
             assert np.array_equal(a[k], b[k]), k
+
+
+@pytest.mark.parametrize("N,tiles", [(256, 3), (512, 2), (1024, 2), (2048, 1)])
+def test_halo_free_pass2_equals_halo_pass2(mw, N, tiles, monkeypatch):
+    """From N = 512 up pass 2 runs without the halo line: a slab's east neighbour column is handed over by the CTA that owns it
+    (csrc/mw_cols_seam.cuh) instead of being transformed a second time.  Same arithmetic on the same inputs: the outputs are
+    bit-identical to the halo kernel's (MW_SEAM=0), frame after frame (the hand-over flags are cleared by pass 1), for every
+    output set that has a whitecap or a Jacobian -- and mw_ocean_sync reports no timed-out hand-over."""
+    res = {}
+    for seam in ("0", "1"):
+        monkeypatch.setenv("MW_SEAM", seam)
+        with mw.Ocean(N, seed=21, tiles=tiles) as o:
+            o.init_spectrum()
+            frames = [o.generate(t, names=("height", "disp", "normal", "whitecap", "jacobian")) for t in (0.0, 1.7, 60.0)]
+            frames.append(o.generate(2.5, names=("whitecap",)))
+            frames.append(o.generate(2.5, names=("height", "disp", "normal")))
+            o.sync()
+            res[seam] = frames
+    for a, b in zip(res["0"], res["1"]):
+        assert a.keys() == b.keys()
+        for k in a:
+            assert np.array_equal(a[k], b[k]), (N, k)
