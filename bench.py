@@ -30,7 +30,7 @@ sys.path.insert(0, ROOT)
 METRIC = "grid-points/sec (spectrum→IFFT→disp+Jacobian) at N×N; achieved HBM GB/s"
 UNIT = "grid-points/s"
 ALG_BYTES_PIPELINE = 44  # read h0+h0conj 16, write height 4 + hds 8 + normal 12 + whitecap 4
-ALG_BYTES_KERNEL = {"spectrum_rows": 16 + 24, "cols_extract": 24 + 28}  # a kernel's own bytes: + the 24 B/pt intermediate
+ALG_BYTES_KERNEL = {"spectrum_rows": 16 + 24, "cols": 24 + 28}  # a kernel's own bytes: + the 24 B/pt intermediate
 NVLINK_NOMINAL_GBS, NVLINK_PEER_COPY_GBS = 900.0, 770.0   # per direction per GPU: nominal / measured peer copy (B200_PROFILING.md)
 
 
@@ -381,7 +381,7 @@ def run_engine(args):
         frame_ms = compute_ms / K
         ach = ALG_BYTES_PIPELINE * pts_rank / (frame_ms * 1e-3) / 1e9
         roof = {
-            "bound": "hbm", "kernel": "k_spectrum_rows + k_cols_extract (one frame = one mw_ocean_generate)",
+            "bound": "hbm", "kernel": "k_spectrum_rows + k_cols_seam (one frame = one mw_ocean_generate)",
             "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4), "traffic": None,
             "peak_source": peak_src, "algorithmic_bytes_per_point": ALG_BYTES_PIPELINE, "points_per_step": pts_rank,
             "algorithmic_bytes_per_step": ALG_BYTES_PIPELINE * pts_rank,
@@ -413,7 +413,7 @@ def run_engine(args):
             kms, kn = prof.kernel_times()
         prof.close()
         del views
-        names = ["spectrum_rows", "cols_extract"]
+        names = ["spectrum_rows", "cols"]   # pass 2 is k_cols_seam from N = 512 up, k_cols_extract below
         per = {names[i]: kms[i] / max(kn[i], 1) for i in range(2)}
         per_step = {names[i]: kms[i] / K for i in range(2)}
         lps = {names[i]: kn[i] / K for i in range(2)}

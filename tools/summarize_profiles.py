@@ -66,7 +66,7 @@ for tag, title in (("frame_grouped", "frame kernels, default scheduling (1 tile 
         if False and tag == "frame_batched":
             def tobytes(x, u):
                 return float(x) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
-            short = "k_cols_extract" if "cols_extract" in name else "k_spectrum_rows"
+            short = "k_cols" if "k_cols" in name else "k_spectrum_rows"
             tot = tobytes(d["dram__bytes_read.sum"], units["dram__bytes_read.sum"]) + tobytes(d["dram__bytes_write.sum"], units["dram__bytes_write.sum"])
             traffic[short] = {"bytes_per_tile": tot / 16.0, "source": f"profiles/{R}_summary.md: dram__bytes_read.sum + dram__bytes_write.sum of one 16-tile launch "
                               "(ncu --set full, MW_GROUP_TILES=16) / 16; a one-tile launch under ncu leaves its writes dirty in L2, so it undercounts"}
