@@ -233,6 +233,26 @@ def extra_configs(mw, torch, stream, peak):
     ocean("config3_1024x1024_single_frame", 1024, 1, all4, 200)
     ocean("config5_one_2048x2048_tile", 2048, 1, all4, 50)
     ocean("config5_four_2048x2048_tiles", 2048, 4, all4, 20)
+    # the reference's own FFT Mesh demo scene (12 x 12, length 12.39: direct-sum kernels) -- what its CPU loop is actually run on
+    o = mw.Ocean(12, length=12.39, seed=1234, device_ptrs=True)
+    o.set_stream(stream.cuda_stream)
+    o.init_spectrum()
+    bufs = {k: torch.empty(144 * comps[k], device="cuda") for k in all4}
+    with torch.cuda.stream(stream):
+        for i in range(10):
+            o.generate(0.016 * i, bufs)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for i in range(200):
+            o.generate(0.016 * i, bufs)
+        e1.record(stream)
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 200
+    o.close()
+    out["fft_mesh_demo_scene_12x12_direct_sum"] = {
+        "resolution": 12, "length": 12.39, "us_per_frame": round(ms * 1e3, 2), "value": 144 / ms * 1e3, "unit": UNIT,
+        "note": "Demo/FFT Mesh.unity:145-152 as shipped: not periodic, so the O(N^4) sum itself runs on the GPU (three launches; a latency figure)"}
     # config 4: Gerstner 32 waves x 1M vertices, L2 flushed between iterations (the 24 MB working set would sit in L2)
     N = 1024
     g = mw.pond_wave_table_32(device_ptrs=True)

@@ -156,6 +156,7 @@ namespace MistralWater.Native
         public const int MW_GATHER_NCCL = 0, MW_GATHER_PEER = 1, MW_GATHER_AUTO = 2, MW_TILES_BLOB_BYTES = 512;
         [DllImport(Lib)] public static extern int mw_tiles_create(ref MwTilesParams p, out IntPtr handle);
         [DllImport(Lib)] public static extern void mw_tiles_destroy(IntPtr handle);
+        [DllImport(Lib)] public static extern int mw_tiles_disconnect(IntPtr handle);
         [DllImport(Lib)] public static extern int mw_tiles_get_layout(IntPtr handle, out MwTilesLayout layout);
         [DllImport(Lib)] public static extern int mw_tiles_export(IntPtr handle, byte[] blob512);
         [DllImport(Lib)] public static extern int mw_tiles_connect(IntPtr handle, byte[] blobsInRankOrder);

@@ -368,6 +368,10 @@ typedef struct mw_tiles mw_tiles; /* opaque */
 
 int mw_tiles_create(const mw_tiles_params* params, mw_tiles** out);
 void mw_tiles_destroy(mw_tiles* t);
+/* One process per GPU: waits for this rank's queued work, then drops its mappings of the peers' buffers and its NCCL
+ * communicator.  Call it on every rank, synchronise the ranks (any barrier the host has), then mw_tiles_destroy: an exported
+ * allocation must not be freed while a peer still maps it.  (mw_tiles_destroy alone does both steps without the barrier.) */
+int mw_tiles_disconnect(mw_tiles* t);
 int mw_tiles_get_layout(const mw_tiles* t, mw_tiles_layout* layout);
 /* One process per GPU only: this rank's blob (MW_TILES_BLOB_BYTES), then all `world` blobs in rank order.  connect() is
  * collective (every rank must call it; it opens the peer mappings, runs a flag handshake, or ncclCommInitRank). */

@@ -394,6 +394,22 @@ extern "C" void mw_tiles_destroy(mw_tiles* t)
     delete t;
 }
 
+extern "C" int mw_tiles_disconnect(mw_tiles* t)
+{
+    if (!t) { mw_set_error("null handle"); return MW_E_INVALID_ARG; }
+    int rc = mw_tiles_sync(t);
+    for (auto& r : t->ranks) {
+        if (r.device < 0) continue;
+        cudaSetDevice(r.device);
+        if (r.comm && nccl_api()->ok) { nccl_api()->CommDestroy(r.comm); r.comm = nullptr; }
+        if (!t->single)
+            for (int p = 0; p < MAXW; ++p)
+                if (r.peer_base[p]) { cudaIpcCloseMemHandle(r.peer_base[p]); r.peer_base[p] = nullptr; }
+    }
+    if (t->world > 1) t->connected = false;
+    return rc;
+}
+
 extern "C" int mw_tiles_get_layout(const mw_tiles* t, mw_tiles_layout* l)
 {
     if (!t || !l) { mw_set_error("null argument"); return MW_E_INVALID_ARG; }

@@ -35,7 +35,7 @@ EXPORTS = (
     "mw_gerstner_displace", "mw_renderer_create", "mw_renderer_destroy", "mw_renderer_render_initial",
     "mw_renderer_set_initial", "mw_renderer_get_initial", "mw_renderer_set_phase", "mw_renderer_get_phase",
     "mw_renderer_set_params", "mw_renderer_generate_texture", "mw_renderer_sync", "mw_mesh_generate", "mw_wave_displace",
-    "mw_tiles_create", "mw_tiles_destroy", "mw_tiles_get_layout", "mw_tiles_export", "mw_tiles_connect",
+    "mw_tiles_create", "mw_tiles_destroy", "mw_tiles_disconnect", "mw_tiles_get_layout", "mw_tiles_export", "mw_tiles_connect",
     "mw_tiles_init_spectrum", "mw_tiles_set_h0", "mw_tiles_set_stream", "mw_tiles_generate_allgather", "mw_tiles_generate_local",
     "mw_tiles_allgather", "mw_tiles_wait", "mw_tiles_sync", "mw_tiles_gather_impl", "mw_tiles_ocean",
 )
@@ -158,6 +158,7 @@ def load() -> C.CDLL:
     lib.mw_tiles_create.argtypes = [C.POINTER(TilesParams), C.POINTER(vp)]
     lib.mw_tiles_destroy.argtypes = [vp]
     lib.mw_tiles_destroy.restype = None
+    lib.mw_tiles_disconnect.argtypes = [vp]
     lib.mw_tiles_get_layout.argtypes = [vp, C.POINTER(TilesLayout)]
     lib.mw_tiles_export.argtypes = [vp, vp]
     lib.mw_tiles_connect.argtypes = [vp, vp]

@@ -181,6 +181,10 @@ class TileSet:
     def sync(self) -> None:
         self._native.check(self._lib.mw_tiles_sync(self._h))
 
+    def disconnect(self) -> None:
+        """Drop the peer mappings / NCCL communicator (then: barrier across ranks, then close())."""
+        self._native.check(self._lib.mw_tiles_disconnect(self._h))
+
     def ocean_handle(self, local_rank: int = 0) -> int:
         return int(self._lib.mw_tiles_ocean(self._h, int(local_rank)) or 0)
 
@@ -313,7 +317,14 @@ class ShardedTiles:
             self.tileset.sync()
 
     def close(self) -> None:
+        """Collective at world > 1: every rank drops its peer mappings, the ranks meet, then the buffers are freed (an
+        exported allocation must not be freed while a peer still maps it)."""
         if self.tileset is not None:
             self.tileset.sync()
+            if self.world > 1:
+                import torch.distributed as dist
+
+                self.tileset.disconnect()
+                dist.barrier(group=self.group)
             self.tileset.close()
             self.tileset = None
