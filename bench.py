@@ -134,7 +134,7 @@ def defaults_for_world(args, world):
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
+    world = max(int(os.environ.get("WORLD_SIZE", "1")), args.gpus)   # the workload is the one the engine arm runs at this N
     if rank != 0:
         return
     defaults_for_world(args, world)
@@ -168,7 +168,7 @@ def run_reference(args):
     emit(line)
 
 
-def workload_config(args, world, gather_impl="peer"):
+def workload_config(args, world):
     N, T = args.resolution, args.tiles
     if world == 1:
         name = (f"{T} x ({N}x{N} Tessendorf grid, height+hds+normal+Jacobian whitecap) per step"
@@ -178,12 +178,9 @@ def workload_config(args, world, gather_impl="peer"):
         name = (f"{world} x {T} independent {N}x{N} ocean tiles, {T} per GPU (seed 1000+tile, wind rotated 45 deg per rank), "
                 f"all-gather of the final float buffers ({T * N * N * 28 / 1e6:.1f} MB per rank)"
                 + (" = BASELINE configs[4]" if (N, T) == (2048, 1) else ""))
-        coll = ("one in-place all-gather of the final float buffers per step over NVLink peer memory: every rank's copy engines "
-                "push its slot into the peers' buffers (CUDA IPC mappings), fenced by stream memory operations on peer flag "
-                "words (cuStreamWriteValue32 / cuStreamWaitValue32) -- no kernel, no SM; the ncclAllGather arm is reported under multi_gpu"
-                if gather_impl in ("peer", "p2p") else
-                "one in-place ncclAllGather of the final float buffers per step (NCCL communicator owned by the tile-set handle); "
-                "the peer-memory arm is reported under multi_gpu")
+        coll = ("one in-place all-gather of the final float buffers per step through the tile-set handle (mw_tiles_*), "
+                "MW_GATHER_AUTO: copy-engine pushes into the peers' buffers (CUDA IPC mappings, fenced by stream memory operations) "
+                "at 2 GPUs, ncclAllGather above; both arms are reported under multi_gpu")
     return {
         "workload": name,
         "resolution": N, "tiles_per_gpu": T, "points_per_step_per_gpu": T * N * N,
@@ -570,7 +567,7 @@ def run_engine(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic (device Philox4x32-10 + Phillips spectrum, seed 1000+tile)",
-            "config": workload_config(args, world, main["impl"]), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+            "config": workload_config(args, world), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roof, "cpu_baseline": cpu,
         }
         if extras is not None:

@@ -91,9 +91,8 @@ def test_bench_helpers_run_without_a_gpu(cref):
     many = argparse.Namespace(resolution=None, tiles=None)
     bench.defaults_for_world(many, 8)
     assert (many.resolution, many.tiles) == (2048, 1)            # N > 1 runs BASELINE configs[4]
-    cfg = bench.workload_config(many, 8, "peer")
-    assert "peer memory" in cfg["collective"] and "configs[4]" in cfg["workload"] and "117.4 MB" in cfg["workload"]
-    assert "ncclAllGather" in bench.workload_config(many, 8, "nccl")["collective"]
+    cfg = bench.workload_config(many, 8)
+    assert "ncclAllGather" in cfg["collective"] and "configs[4]" in cfg["workload"] and "117.4 MB" in cfg["workload"]
     solo = argparse.Namespace(resolution=None, tiles=None)
     bench.defaults_for_world(solo, 1)
     assert (solo.resolution, solo.tiles) == (1024, 16)
