@@ -96,7 +96,6 @@ NcclApi* nccl_api()
 typedef CUresult (*MemOp32Fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
 struct MemOps {
     MemOp32Fn write32 = nullptr, wait32 = nullptr;
-    CUresult (*addr_range)(CUdeviceptr*, size_t*, CUdeviceptr) = nullptr;
     bool ok = false;
 };
 MemOps* memops()
@@ -182,8 +181,6 @@ struct mw_tiles {
     uint32_t frames = 0;     // frames generated so far
     uint32_t gathers = 0;    // gathers enqueued so far (sequence number of the flag protocol)
     int buf_of_frame[2] = {0, 0};  // [0] latest frame's buffer, [1] the one before
-    ncclUniqueId nccl_id;
-    bool have_id = false;
 };
 
 namespace {
@@ -370,7 +367,8 @@ extern "C" int mw_tiles_create(const mw_tiles_params* params, mw_tiles** out)
     t->nlocal = t->single ? p.world : 1;
     t->impl = gather;
     t->async = (p.flags & MW_TILES_ASYNC) != 0;
-    if (const char* e = getenv("MW_TILES_PUSH_LANES")) t->push_lanes = atoi(e);
+    if (const char* e = getenv("MW_TILES_PUSH_LANES")) t->push_lanes = atoi(e);   // (experiment knob, tools/gather_probe.py)
+    if (t->push_lanes > p.world - 1) t->push_lanes = p.world - 1;
     t->n2 = (size_t)t->N * t->N;
     t->slot_floats = (size_t)t->tpr * t->n2 * 7;
     t->flags_off = ((size_t)2 * t->world * t->slot_floats * sizeof(float) + 255) & ~(size_t)255;
