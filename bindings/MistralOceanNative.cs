@@ -90,7 +90,7 @@ namespace MistralWater.Native
         public int gather;                 // MW_GATHER_NCCL = 0, MW_GATHER_PEER = 1, MW_GATHER_AUTO = 2
         [MarshalAs(UnmanagedType.ByValArray, SizeConst = 16)] public int[] devices;
         public float windStepDeg;          // config 5: 45
-        public uint flags;                 // MW_TILES_ASYNC = 1
+        public uint flags;                 // MW_TILES_ASYNC = 1 | one of MW_TILES_PUSH_CE = 2, _SM = 4, _TMA = 8 (default)
     }
 
     [StructLayout(LayoutKind.Sequential)]
@@ -154,6 +154,7 @@ namespace MistralWater.Native
         // multi-GPU tile sets (no reference counterpart): the handle owns gather buffers, streams, peer mappings and NCCL
         // communicators; rank = -1 drives all GPUs from this one process (ncclCommInitAll / peer copies fenced by events)
         public const int MW_GATHER_NCCL = 0, MW_GATHER_PEER = 1, MW_GATHER_AUTO = 2, MW_TILES_BLOB_BYTES = 512;
+        public const uint MW_TILES_ASYNC = 1, MW_TILES_PUSH_CE = 2, MW_TILES_PUSH_SM = 4, MW_TILES_PUSH_TMA = 8;
         [DllImport(Lib)] public static extern int mw_tiles_create(ref MwTilesParams p, out IntPtr handle);
         [DllImport(Lib)] public static extern void mw_tiles_destroy(IntPtr handle);
         [DllImport(Lib)] public static extern int mw_tiles_disconnect(IntPtr handle);

@@ -342,7 +342,14 @@ enum {
                           (4 GPUs 0.64 vs 0.87 ms, 8 GPUs 1.32 vs 2.20 ms: concurrent copy-engine pushes to several peers reach
                           only ~370-420 GB/s there, NCCL 570-630 GB/s); peer if NCCL cannot be loaded */
 };
-enum { MW_TILES_ASYNC = 1u << 0 /* generate_allgather only enqueues; mw_tiles_wait / mw_tiles_sync order the results */ };
+enum {
+    MW_TILES_ASYNC = 1u << 0,   /* generate_allgather only enqueues; mw_tiles_wait / mw_tiles_sync order the results        */
+    /* MW_GATHER_PEER: what moves a rank's slot into its peers' buffers (none of the three = MW_TILES_PUSH_TMA)             */
+    MW_TILES_PUSH_CE = 1u << 1, /* one copy-engine transfer per peer (cudaMemcpyAsync / cudaMemcpyPeerAsync)                */
+    MW_TILES_PUSH_SM = 1u << 2, /* one kernel: 16-byte loads, (world - 1) 16-byte stores through the peer mappings          */
+    MW_TILES_PUSH_TMA = 1u << 3 /* one kernel: a ring of cp.async.bulk global -> shared -> (world - 1) peers per CTA, driven
+                                   by one thread; the default                                                              */
+};
 
 typedef struct mw_tiles_params {
     mw_ocean_params ocean;   /* per-tile parameters; .tiles and .device are ignored (tiles_per_rank / devices[] below),
@@ -353,7 +360,7 @@ typedef struct mw_tiles_params {
     int32_t gather;          /* MW_GATHER_NCCL | MW_GATHER_PEER | MW_GATHER_AUTO                                        */
     int32_t devices[MW_TILES_MAX_WORLD]; /* CUDA ordinal of rank r (rank >= 0: only devices[rank] is read)              */
     float wind_step_deg;     /* config 5: 45                                                                            */
-    uint32_t flags;          /* MW_TILES_ASYNC                                                                          */
+    uint32_t flags;          /* MW_TILES_ASYNC | one of MW_TILES_PUSH_*                                                 */
 } mw_tiles_params;
 
 typedef struct mw_tiles_layout {

@@ -132,7 +132,91 @@ __global__ void k_flag_write(uint32_t* flag, uint32_t value)
     __threadfence_system();
 }
 
+// SM-side push (MW_TILES_PUSH=sm): one kernel reads this rank's slot once and stores it into every peer's gather buffer through
+// the peer mappings -- (world - 1) 16-byte stores per 16-byte load, a few CTAs wide, running beside the frame kernels.  The
+// alternative to one copy-engine transfer per peer, which reaches only 370-420 GB/s on this pool once several flows run at once.
+struct PushArgs {
+    const float4* src;
+    float4* dst[MW_TILES_MAX_WORLD];
+    int npeers;
+    unsigned long long n16;   // 16-byte elements per slot
+};
+__global__ void __launch_bounds__(512) k_push_slots(const __grid_constant__ PushArgs a)
+{
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < a.n16; i += 4 * stride) {
+        float4 v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = ldg_stream4(a.src + i + k * stride);
+        for (int p = 0; p < a.npeers; ++p) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) a.dst[p][i + k * stride] = v[k];
+        }
+    }
+    for (; i < a.n16; i += stride) {
+        const float4 v = ldg_stream4(a.src + i);
+        for (int p = 0; p < a.npeers; ++p) a.dst[p][i] = v;
+    }
+}
+
+
+// Bulk-copy push (MW_TILES_PUSH=tma): the same transfer driven by the TMA unit instead of by load/store instructions.  One
+// thread per CTA runs a ring of PUSH_STAGES shared-memory stages: cp.async.bulk global -> shared of a chunk of this rank's
+// slot (mbarrier completion), then (world - 1) cp.async.bulk shared -> peer global of the same chunk as one bulk group; a stage is
+// reloaded as soon as the group that read it has drained (wait_group.read), so loads, the stores of the previous chunk and
+// the fabric's own queues overlap.  Chunks are dealt to the CTAs round-robin: at any moment the grid works on one contiguous
+// window of the slot.  No register, LSU or issue-slot traffic on the SMs that host it.
+constexpr int PUSH_STAGES = 4;
+struct PushBulkArgs {
+    const char* src;
+    char* dst[MW_TILES_MAX_WORLD];
+    int npeers;
+    unsigned chunk;             // bytes per chunk (multiple of 16)
+    unsigned long long bytes;   // bytes per slot (multiple of 16)
+};
+__device__ __forceinline__ void bulk_s2g(void* gdst, const void* smem_src, unsigned bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
+}
+__global__ void __launch_bounds__(32) k_push_slots_bulk(const __grid_constant__ PushBulkArgs a)
+{
+    extern __shared__ __align__(128) unsigned char stage_mem[];
+    __shared__ uint64_t full[PUSH_STAGES];
+    if (threadIdx.x != 0) return;
+#pragma unroll
+    for (int s = 0; s < PUSH_STAGES; ++s) mbar_init(&full[s], 1);
+    const unsigned long long nchunks = (a.bytes + a.chunk - 1) / a.chunk;
+    const unsigned long long mine = nchunks > blockIdx.x ? (nchunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    auto chunk_off = [&](unsigned long long k) { return (blockIdx.x + k * gridDim.x) * (unsigned long long)a.chunk; };
+    auto chunk_len = [&](unsigned long long off) { return (unsigned)((a.bytes - off) < a.chunk ? (a.bytes - off) : a.chunk); };
+    auto load = [&](unsigned long long k) {
+        const int s = (int)(k % PUSH_STAGES);
+        const unsigned long long off = chunk_off(k);
+        const unsigned len = chunk_len(off);
+        mbar_expect_tx(&full[s], len);
+        bulk_g2s(stage_mem + (size_t)s * a.chunk, a.src + off, len, &full[s]);
+    };
+    for (unsigned long long k = 0; k < PUSH_STAGES && k < mine; ++k) load(k);
+    for (unsigned long long k = 0; k < mine; ++k) {
+        const int s = (int)(k % PUSH_STAGES);
+        mbar_wait(&full[s], (unsigned)((k / PUSH_STAGES) & 1));
+        const unsigned long long off = chunk_off(k);
+        const unsigned len = chunk_len(off);
+        for (int p = 0; p < a.npeers; ++p) bulk_s2g(a.dst[p] + off, stage_mem + (size_t)s * a.chunk, len);
+        bulk_commit();
+        if (k >= 1 && k - 1 + PUSH_STAGES < mine) {
+            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // chunk k-1's stores have read their stage
+            load(k - 1 + PUSH_STAGES);
+        }
+    }
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // every store of this CTA is complete, not only read
+    __threadfence_system();
+}
+
 constexpr int MAXW = MW_TILES_MAX_WORLD;
+enum { PUSH_CE = 0, PUSH_SM = 1, PUSH_TMA = 2 };
+constexpr int AUTO_PEER_MAX_WORLD = MW_TILES_MAX_WORLD;   // MW_GATHER_AUTO: the peer pushes up to this many ranks, ncclAllGather above
 constexpr uint32_t BLOB_MAGIC = 0x4d575432u;  // "MWT2"
 // flag words of one rank (uint32), written by its peers through their mappings
 struct FlagWords {
@@ -176,6 +260,9 @@ struct mw_tiles {
     bool single = true, connected = false, async = false;
     bool kernel_flags = false;   // peer flag writes by k_flag_write instead of cuStreamWriteValue32
     int push_lanes = 0;          // MW_TILES_PUSH_LANES: 0 = one copy stream per peer; k > 0 = the pushes share k streams
+    int push_mode = PUSH_TMA;    // how a rank's slot reaches its peers: mw_tiles_params.flags, or MW_TILES_PUSH=ce|sm|tma
+    int push_ctas = 0;           // CTAs of the push kernel (MW_TILES_PUSH_CTAS; default by world, see mw_tiles_create)
+    unsigned push_chunk = 16384; // MW_TILES_PUSH_CHUNK: bytes per bulk-copy chunk (tma)
     size_t n2 = 0, slot_floats = 0, alloc_bytes = 0, flags_off = 0;
     std::vector<TileRank> ranks;
     uint32_t frames = 0;     // frames generated so far
@@ -218,9 +305,14 @@ int create_rank(mw_tiles* t, TileRank& r, int rank, int device)
     MW_CUDA(cudaStreamCreateWithFlags(&r.s_flag, cudaStreamNonBlocking));
     r.s_user = r.s_user_own;
     if ((rc = mw_ocean_set_stream(r.ocean, r.s_gen))) return rc;
+    int prio_least = 0, prio_greatest = 0;
+    MW_CUDA(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
+    const char* pe = getenv("MW_TILES_PUSH_PRIO");   // developer knob: 0 = default priority
+    const int push_prio = (pe && atoi(pe) == 0) ? 0 : prio_greatest;
     for (int p = 0; p < t->world; ++p) {
         if (p == rank) continue;
-        MW_CUDA(cudaStreamCreateWithFlags(&r.s_push[p], cudaStreamNonBlocking));
+        // the gather is the critical path of a multi-GPU step: its copies / push kernels go ahead of queued frame kernels
+        MW_CUDA(cudaStreamCreateWithPriority(&r.s_push[p], cudaStreamNonBlocking, push_prio));
         if ((rc = make_event(&r.ev_push[p]))) return rc;
     }
     if ((rc = make_event(&r.ev_user))) return rc;
@@ -351,7 +443,9 @@ extern "C" int mw_tiles_create(const mw_tiles_params* params, mw_tiles** out)
         return MW_E_INVALID_ARG;
     }
     // MW_GATHER_AUTO: see include/mistral_ocean.h -- every rank of a node resolves it the same way
-    const int gather = p.gather != MW_GATHER_AUTO ? p.gather : ((p.world <= 2 || !nccl_api()->ok) ? MW_GATHER_PEER : MW_GATHER_NCCL);
+    const bool peer_usable = p.rank < 0 || memops()->ok;   // between processes the flag protocol needs stream memory operations
+    const int gather = p.gather != MW_GATHER_AUTO ? p.gather
+                     : ((peer_usable && p.world <= AUTO_PEER_MAX_WORLD) || !nccl_api()->ok) ? MW_GATHER_PEER : MW_GATHER_NCCL;
     if (gather == MW_GATHER_NCCL && p.world > 1 && !nccl_api()->ok) { mw_set_error("MW_GATHER_NCCL: %s", nccl_api()->why); return MW_E_NCCL; }
     if (gather == MW_GATHER_PEER && p.rank >= 0 && p.world > 1 && !memops()->ok) {
         mw_set_error("MW_GATHER_PEER between processes needs cuStreamWriteValue32 / cuStreamWaitValue32");
@@ -369,6 +463,17 @@ extern "C" int mw_tiles_create(const mw_tiles_params* params, mw_tiles** out)
     t->async = (p.flags & MW_TILES_ASYNC) != 0;
     if (const char* e = getenv("MW_TILES_PUSH_LANES")) t->push_lanes = atoi(e);   // (experiment knob, tools/gather_probe.py)
     if (t->push_lanes > p.world - 1) t->push_lanes = p.world - 1;
+    t->push_mode = (p.flags & MW_TILES_PUSH_CE) ? PUSH_CE : (p.flags & MW_TILES_PUSH_SM) ? PUSH_SM : PUSH_TMA;
+    // developer overrides (tools/gather_probe.py, tools/push_call.sh)
+    if (const char* e = getenv("MW_TILES_PUSH")) t->push_mode = !strcmp(e, "sm") ? PUSH_SM : !strcmp(e, "tma") ? PUSH_TMA : PUSH_CE;
+    // Enough CTAs to keep the links busy and no more: every SM that hosts a push CTA is lost to pass 2 (whose CTAs take a
+    // whole register file).  Measured on B200 / NVSwitch (profiles/r02_push_probe_*.jsonl).
+    t->push_ctas = t->push_mode == PUSH_SM ? 32 : (p.world <= 2 ? 32 : 64);
+    if (const char* e = getenv("MW_TILES_PUSH_CTAS")) if (atoi(e) > 0) t->push_ctas = atoi(e);
+    if (const char* e = getenv("MW_TILES_PUSH_CHUNK")) {
+        const int c = atoi(e) & ~15;
+        if (c >= 1024 && c * PUSH_STAGES <= 200 * 1024) t->push_chunk = (unsigned)c;
+    }
     t->n2 = (size_t)t->N * t->N;
     t->slot_floats = (size_t)t->tpr * t->n2 * 7;
     t->flags_off = ((size_t)2 * t->world * t->slot_floats * sizeof(float) + 255) & ~(size_t)255;
@@ -579,6 +684,31 @@ int enqueue_generate(mw_tiles* t, int b, float time)
     return MW_OK;
 }
 
+// launch the kernel push of `src` (slot_bytes) into dst[0 .. npeers) on stream s
+int launch_push(mw_tiles* t, int push, cudaStream_t s, const float* src, char* const* dst, int npeers, size_t slot_bytes)
+{
+    if (push == PUSH_SM) {
+        PushArgs pa;
+        pa.src = reinterpret_cast<const float4*>(src);
+        pa.npeers = npeers;
+        pa.n16 = (unsigned long long)(slot_bytes / 16);
+        for (int i = 0; i < npeers; ++i) pa.dst[i] = reinterpret_cast<float4*>(dst[i]);
+        k_push_slots<<<t->push_ctas, 512, 0, s>>>(pa);
+    } else {
+        PushBulkArgs pa;
+        pa.src = reinterpret_cast<const char*>(src);
+        pa.npeers = npeers;
+        pa.chunk = t->push_chunk;
+        pa.bytes = (unsigned long long)slot_bytes;
+        for (int i = 0; i < npeers; ++i) pa.dst[i] = dst[i];
+        const size_t smem = (size_t)PUSH_STAGES * t->push_chunk;
+        MW_CUDA(cudaFuncSetAttribute(k_push_slots_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_push_slots_bulk<<<t->push_ctas, 32, smem, s>>>(pa);
+    }
+    MW_LAUNCH_CHECK();
+    return MW_OK;
+}
+
 int enqueue_gather(mw_tiles* t, int b)
 {
     if (t->world == 1) {
@@ -592,6 +722,8 @@ int enqueue_gather(mw_tiles* t, int b)
     }
     const uint32_t seq = ++t->gathers;
     const size_t slot_bytes = t->slot_floats * sizeof(float);
+    // the kernel pushes move 16-byte units: slots of odd grids (direct-sum path) keep the copy engines
+    const int push = (slot_bytes % 16 == 0) ? t->push_mode : PUSH_CE;
     // The user stream's position at this call bounds the readers of buffer b that the gather must not overtake.  The
     // "free" announcement travels on its own stream: it must not queue behind the previous gather's completion waits on
     // s_comm, or every step would pay a flag round trip between two gathers.  (Announcing before the previous gather into
@@ -624,6 +756,22 @@ int enqueue_gather(mw_tiles* t, int b)
         for (auto& r : t->ranks) {
             MW_CUDA(cudaSetDevice(r.device));
             const float* src = r.gather[b] + (size_t)r.rank * t->slot_floats;
+            if (push != PUSH_CE) {
+                // one push kernel per source rank, storing through the peer-access mappings
+                cudaStream_t s = r.s_push[(r.rank + 1) % t->world];
+                char* dst[MAXW];
+                int npeers = 0;
+                if (r.gen_used[b]) MW_CUDA(cudaStreamWaitEvent(s, r.ev_gen[b], 0));
+                for (int j = 1; j < t->world; ++j) {
+                    const int p = (r.rank + j) % t->world;
+                    MW_CUDA(cudaStreamWaitEvent(s, t->ranks[p].ev_free[b], 0));
+                    dst[npeers++] = reinterpret_cast<char*>(t->ranks[p].gather[b] + (size_t)r.rank * t->slot_floats);
+                }
+                int rc = launch_push(t, push, s, src, dst, npeers, slot_bytes);
+                if (rc) return rc;
+                for (int p = 0; p < t->world; ++p) if (p != r.rank) MW_CUDA(cudaEventRecord(r.ev_push[p], s));
+                continue;
+            }
             for (int j = 1; j < t->world; ++j) {
                 const int p = (r.rank + j) % t->world;
                 TileRank& dst = t->ranks[p];
@@ -656,6 +804,25 @@ int enqueue_gather(mw_tiles* t, int b)
             if (rc) return rc;
         }
         const float* src = r.gather[b] + (size_t)r.rank * t->slot_floats;
+        if (push != PUSH_CE) {
+            // one kernel on the first push stream: waits for every peer's "free", stores the slot into all of them, signals all
+            cudaStream_t s = r.s_push[(r.rank + 1) % t->world];
+            char* dst[MAXW];
+            int npeers = 0;
+            if (r.gen_used[b]) MW_CUDA(cudaStreamWaitEvent(s, r.ev_gen[b], 0));
+            for (int j = 1; j < t->world; ++j) {
+                const int p = (r.rank + j) % t->world;
+                MW_CU(m->wait32((CUstream)s, (CUdeviceptr)&r.flags->free_[b][p], seq, CU_STREAM_WAIT_VALUE_GEQ));
+                dst[npeers++] = reinterpret_cast<char*>(r.peer_gather[b][p] + (size_t)r.rank * t->slot_floats);
+            }
+            { int rc = launch_push(t, push, s, src, dst, npeers, slot_bytes); if (rc) return rc; }
+            for (int j = 1; j < t->world; ++j) {
+                const int p = (r.rank + j) % t->world;
+                int rc = flag_write(t, s, &r.peer_flags[p]->landed[b][r.rank], seq);
+                if (rc) return rc;
+                MW_CUDA(cudaEventRecord(r.ev_push[p], s));
+            }
+        } else
         for (int j = 1; j < t->world; ++j) {
             const int p = (r.rank + j) % t->world;
             cudaStream_t s = push_stream(t, r, p, j);

@@ -43,6 +43,7 @@ MW_TILES_MAX_WORLD = 16
 MW_TILES_BLOB_BYTES = 512
 MW_GATHER_NCCL, MW_GATHER_PEER, MW_GATHER_AUTO = 0, 1, 2
 MW_TILES_ASYNC = 1 << 0
+MW_TILES_PUSH_CE, MW_TILES_PUSH_SM, MW_TILES_PUSH_TMA = 1 << 1, 1 << 2, 1 << 3
 
 
 class MwError(RuntimeError):

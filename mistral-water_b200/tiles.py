@@ -82,7 +82,7 @@ class TileSet:
     def __init__(self, N: int, world: int, rank: int | None = None, devices=None, tiles_per_rank: int = 1,
                  gather: str = "auto", base_seed: int = 1000, wind=(5.0, 3.0), amplitude: float = 0.01,
                  unit_width: float = 1.0, choppiness: float = 1.0, wind_step_deg: float = 45.0, asynchronous: bool = True,
-                 profile: bool = False, exchange=None):
+                 profile: bool = False, exchange=None, push: str = "tma"):
         import ctypes as C
 
         import numpy as np
@@ -103,7 +103,8 @@ class TileSet:
         for i, d in enumerate(devices[:native.MW_TILES_MAX_WORLD]):
             p.devices[i] = int(d)
         p.wind_step_deg = float(wind_step_deg)
-        p.flags = native.MW_TILES_ASYNC if asynchronous else 0
+        p.flags = (native.MW_TILES_ASYNC if asynchronous else 0) | {"ce": native.MW_TILES_PUSH_CE, "sm": native.MW_TILES_PUSH_SM,
+                                                                  "tma": native.MW_TILES_PUSH_TMA}[push]
         self.devices = devices
         self._h = C.c_void_p()
         native.check(self._lib.mw_tiles_create(C.byref(p), C.byref(self._h)))

@@ -12,8 +12,9 @@ dist.init_process_group("nccl", device_id=dev)
 from mistral_water_b200.tiles import ShardedTiles
 
 N, T, K = int(os.environ.get("MW_PROBE_N", "2048")), int(os.environ.get("MW_PROBE_TILES", "1")), 40
-res = {"world": world, "N": N, "tiles": T, "lanes": os.environ.get("MW_TILES_PUSH_LANES", ""), "maxconn": os.environ.get("CUDA_DEVICE_MAX_CONNECTIONS", "")}
-for arm in ("peer", "nccl"):
+res = {"world": world, "N": N, "tiles": T, "lanes": os.environ.get("MW_TILES_PUSH_LANES", ""), "maxconn": os.environ.get("CUDA_DEVICE_MAX_CONNECTIONS", ""),
+       "push": os.environ.get("MW_TILES_PUSH", "ce"), "push_ctas": os.environ.get("MW_TILES_PUSH_CTAS", ""), "push_chunk": os.environ.get("MW_TILES_PUSH_CHUNK", ""), "prio": os.environ.get("MW_TILES_PUSH_PRIO", "")}
+for arm in os.environ.get("MW_PROBE_ARMS", "peer,nccl").split(","):
     st = ShardedTiles(N, rank, world, tiles_per_rank=T, device=dev, gather=arm)
     with torch.cuda.stream(st.stream):
         st.generate_local(0.0); st.finish()
@@ -30,10 +31,10 @@ for arm in ("peer", "nccl"):
         for k in range(3): st.generate_pipelined(0.1 * k)
         st.finish(); torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
         e0.record(st.stream)
-        for k in range(K): st.generate_pipelined(0.016 * k)
+        for k in range(3 * K): st.generate_pipelined(0.016 * k)
         st.finish(); e1.record(st.stream)
         torch.cuda.synchronize(); dist.barrier()
-        t = torch.tensor([e0.elapsed_time(e1) / K], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t = torch.tensor([e0.elapsed_time(e1) / (3 * K)], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX)
     slot = st.layout.slot_bytes
     res[arm] = {"gather_ms": round(ms, 4), "busbw_gbs": round(slot * (world - 1) / ms / 1e6, 1), "step_ms": round(float(t.item()), 4)}
     st.close(); dist.barrier()
