@@ -179,8 +179,8 @@ def workload_config(args, world):
                 f"all-gather of the final float buffers ({T * N * N * 28 / 1e6:.1f} MB per rank)"
                 + (" = BASELINE configs[4]" if (N, T) == (2048, 1) else ""))
         coll = ("one in-place all-gather of the final float buffers per step through the tile-set handle (mw_tiles_*), "
-                "MW_GATHER_AUTO: copy-engine pushes into the peers' buffers (CUDA IPC mappings, fenced by stream memory operations) "
-                "at 2 GPUs, ncclAllGather above; both arms are reported under multi_gpu")
+                "MW_GATHER_AUTO: every rank pushes its slot into the peers' buffers with a TMA bulk-copy kernel (CUDA IPC mappings, fenced "
+                "by stream memory operations); the ncclAllGather arm is measured beside it and both are reported under multi_gpu")
     return {
         "workload": name,
         "resolution": N, "tiles_per_gpu": T, "points_per_step_per_gpu": T * N * N,
@@ -387,7 +387,7 @@ def run_engine(args):
         st.sync()
         return st, res
 
-    st, main = measure_arm("auto")     # MW_GATHER_AUTO: peer pushes at 2 GPUs, ncclAllGather above (include/mistral_ocean.h)
+    st, main = measure_arm("auto")     # MW_GATHER_AUTO: the peer pushes (include/mistral_ocean.h)
     ms, compute_ms, clocks, launches = main["ms"], main["compute_ms"], main["clocks"], main["launches"]
     value = world * pts_rank * K / (ms * 1e-3)
     stream = st.stream
@@ -588,7 +588,7 @@ def run_engine(args):
                                       f"ingress: {NVLINK_NOMINAL_GBS:.0f} GB/s nominal, {NVLINK_PEER_COPY_GBS:.0f} GB/s measured peer copy",
                 "value_ceiling_at_floor": world * pts_rank / (max(floor_nom, compute_ms / K) * 1e-3),
                 "arms": {main["impl"]: arm(main), other["impl"]: arm(other)},
-                "default_arm": main["impl"], "default_arm_rule": "MW_GATHER_AUTO: peer-memory pushes at 2 GPUs, ncclAllGather above",
+                "default_arm": main["impl"], "default_arm_rule": "MW_GATHER_AUTO: peer-memory pushes (TMA bulk-copy kernel) at every world size; ncclAllGather if peer memory is unusable",
                 "rank0_numa_binding": numa,
             }
         emit(line)

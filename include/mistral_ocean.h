@@ -319,15 +319,17 @@ int mw_wave_displace(const mw_wave_params* p, const float* pos_xyz, float* out_x
  *
  * Two process models, one API:
  *   single process (rank == -1)   the reference's host model (one Unity process): the handle drives all `world` devices --
- *                                 ncclCommInitAll + grouped ncclAllGather, or peer copies fenced by CUDA events;
+ *                                 ncclCommInitAll + grouped ncclAllGather, or peer pushes fenced by CUDA events;
  *   one process per GPU (rank>=0) each process creates its rank, then the ranks swap fixed-size blobs (CUDA IPC handles of
  *                                 the gather buffers and flag words; rank 0's blob carries the ncclUniqueId) by whatever
  *                                 means the host has -- mw_tiles_export / mw_tiles_connect.
  * Two ways to carry out the all-gather (`gather`):
  *   MW_GATHER_NCCL  one in-place ncclAllGather per frame (libnccl.so.2 is loaded at run time; absent => MW_E_NCCL);
- *   MW_GATHER_PEER  every rank pushes its slot into the peers' buffers over NVLink with the copy engines -- no SM is taken
- *                   from the frame kernels.  Ranks in different processes are fenced by stream memory operations on flag
- *                   words in peer memory (cuStreamWriteValue32 / cuStreamWaitValue32): no kernel, no host round trip.
+ *   MW_GATHER_PEER  every rank pushes its slot into the peers' buffers over NVLink (peer access inside a process, CUDA IPC
+ *                   mappings between processes): by default one small kernel per rank and frame whose CTAs each run a ring
+ *                   of TMA bulk copies global -> shared -> every peer (MW_TILES_PUSH_TMA), or copy-engine transfers / plain
+ *                   stores (MW_TILES_PUSH_CE / _SM).  Ranks in different processes are fenced by stream memory operations on
+ *                   flag words in peer memory (cuStreamWriteValue32 / cuStreamWaitValue32): no host round trip.
  * Frames are double-buffered: the gather of frame k (communication streams) runs under the generation of frame k + 1.
  * Contract for the returned buffers: the buffer of frame k is rewritten by frame k + 2; all reads of it must have been
  * enqueued on the user stream (mw_tiles_set_stream; default: the handle's own) before the call that generates frame k + 2.
@@ -337,10 +339,10 @@ int mw_wave_displace(const mw_wave_params* p, const float* pos_xyz, float* out_x
 enum {
     MW_GATHER_NCCL = 0,
     MW_GATHER_PEER = 1,
-    MW_GATHER_AUTO = 2 /* what measured fastest on 8 x B200 / NVSwitch (profiles/r02_bench_{2,4,8}gpu.json): the peer pushes for
-                          world <= 2 (one flow per link direction: 0.24 vs 0.31 ms per 2048^2 step), ncclAllGather above
-                          (4 GPUs 0.64 vs 0.87 ms, 8 GPUs 1.32 vs 2.20 ms: concurrent copy-engine pushes to several peers reach
-                          only ~370-420 GB/s there, NCCL 570-630 GB/s); peer if NCCL cannot be loaded */
+    MW_GATHER_AUTO = 2 /* what measured fastest on 8 x B200 / NVSwitch (profiles/r02_push_probe_{2,4,8}gpu.jsonl, r02_bench_8gpu.json):
+                          the peer pushes with the TMA kernel at every world size (2048^2 step at 2 / 4 / 8 GPUs: 0.21 / 0.54 /
+                          1.28 ms against 0.37 / 0.64 / 1.45 ms with ncclAllGather); ncclAllGather if stream memory operations
+                          are unavailable between processes, peer if NCCL cannot be loaded */
 };
 enum {
     MW_TILES_ASYNC = 1u << 0,   /* generate_allgather only enqueues; mw_tiles_wait / mw_tiles_sync order the results        */

@@ -8,10 +8,11 @@
 //   * the gather of frame k runs on communication streams under the generation of frame k + 1;
 //   * MW_GATHER_NCCL: ncclAllGather in place (libnccl.so.2 resolved with dlopen: the library carries no link-time
 //     dependency on NCCL and reports MW_E_NCCL when it is absent);
-//   * MW_GATHER_PEER: one copy-engine push per peer over NVLink (peer access inside a process, CUDA IPC mappings between
-//     processes).  Between processes the ranks are fenced by stream memory operations on flag words that live in the
+//   * MW_GATHER_PEER: every rank pushes its slot into the peers' buffers over NVLink (peer access inside a process, CUDA IPC
+//     mappings between processes) -- k_push_slots_bulk (TMA bulk copies, default), k_push_slots (SM stores) or one copy-engine
+//     transfer per peer.  Between processes the ranks are fenced by stream memory operations on flag words that live in the
 //     exported allocation: "my buffer b is free" (cuStreamWriteValue32 into every peer) before a push may start
-//     (cuStreamWaitValue32 on the local copy), "my slot has landed" after it.  No kernel, no host round trip.
+//     (cuStreamWaitValue32 on the local copy), "my slot has landed" after it.  No host round trip.
 #include <dlfcn.h>
 #include <math.h>
 #include <nccl.h>  // types and prototypes only: every NCCL entry point is resolved at run time
