@@ -224,8 +224,11 @@ extern "C" int mw_renderer_set_params(mw_renderer* r, float length, float choppi
     return MW_OK;
 }
 
+#ifndef MW_RMAPS_PER_GROUP
+#define MW_RMAPS_PER_GROUP 1   // k_r_maps right behind each tile group's k_r_cols (its two images still in L2); 0 = one launch at the end
+#endif
 template <int N>
-static int run_renderer_frame(mw_renderer* r, float dt, float4* d_disp, float4* d_height)
+static int run_renderer_frame(mw_renderer* r, float dt, float4* d_disp, float4* d_height, const mwr::RMapArgs* maps)
 {
     using P = mwfft::Plan<N>;
     constexpr int T = P::T;
@@ -260,6 +263,13 @@ static int run_renderer_frame(mw_renderer* r, float dt, float4* d_disp, float4* 
         mwr::RColArgs ca{xab, xc, r->twimg, d_disp, d_height, t0, N / W};
         MW_CUDA(mw_launch(mwr::k_r_cols<N>, dim3(N / W + N / (2 * W), nt), W * T, smem_c, st, r->pdl, ca));
         MW_LAUNCH_CHECK();
+        if (maps && MW_RMAPS_PER_GROUP) {
+            // pass 3 of this group straight away: the group's displacement / height images (32 B per texel) are still in L2
+            mwr::RMapArgs ma = *maps;
+            ma.tile0 = t0;
+            MW_CUDA(mw_launch(mwr::k_r_maps, dim3((N + 31) / 32, (N + 7) / 8, nt), 256, 0, st, r->pdl, ma));
+            MW_LAUNCH_CHECK();
+        }
     }
     if (dual) {
         MW_CUDA(cudaEventRecord(r->ev_join, r->aux_stream));
@@ -294,20 +304,21 @@ extern "C" int mw_renderer_generate_texture(mw_renderer* r, float delta_time, co
     if (out->jacobian) { if (dev) d_jac = out->jacobian; else { if ((rc = r_ensure(&r->s_jac, total))) return rc; d_jac = r->s_jac; } }
 
     volatile float dt = delta_time * r->p.mult;  // OceanRenderer.cs:223
+    const mwr::RMapArgs ma{d_disp, d_height, d_normal, d_white, d_white4, d_jac, r->R, 0, r->R / r->p.resolution,
+                           (r->p.flags & MW_WRAP_REPEAT) ? 1 : 0, r->p.length / (float)r->R};
+    const mwr::RMapArgs* mp = (d_normal || want_white) ? &ma : nullptr;
     switch (r->R) {
-        case 32: rc = run_renderer_frame<32>(r, dt, d_disp, d_height); break;
-        case 64: rc = run_renderer_frame<64>(r, dt, d_disp, d_height); break;
-        case 128: rc = run_renderer_frame<128>(r, dt, d_disp, d_height); break;
-        case 256: rc = run_renderer_frame<256>(r, dt, d_disp, d_height); break;
-        case 512: rc = run_renderer_frame<512>(r, dt, d_disp, d_height); break;
-        case 1024: rc = run_renderer_frame<1024>(r, dt, d_disp, d_height); break;
-        case 2048: rc = run_renderer_frame<2048>(r, dt, d_disp, d_height); break;
+        case 32: rc = run_renderer_frame<32>(r, dt, d_disp, d_height, mp); break;
+        case 64: rc = run_renderer_frame<64>(r, dt, d_disp, d_height, mp); break;
+        case 128: rc = run_renderer_frame<128>(r, dt, d_disp, d_height, mp); break;
+        case 256: rc = run_renderer_frame<256>(r, dt, d_disp, d_height, mp); break;
+        case 512: rc = run_renderer_frame<512>(r, dt, d_disp, d_height, mp); break;
+        case 1024: rc = run_renderer_frame<1024>(r, dt, d_disp, d_height, mp); break;
+        case 2048: rc = run_renderer_frame<2048>(r, dt, d_disp, d_height, mp); break;
         default: mw_set_error("unsupported texture resolution %d", r->R); return MW_E_INVALID_ARG;
     }
     if (rc) return rc;
-    if (d_normal || want_white) {
-        mwr::RMapArgs ma{d_disp, d_height, d_normal, d_white, d_white4, d_jac, r->R, r->tiles, r->R / r->p.resolution,
-                         (r->p.flags & MW_WRAP_REPEAT) ? 1 : 0, r->p.length / (float)r->R};
+    if (mp && !MW_RMAPS_PER_GROUP) {
         MW_CUDA(mw_launch(mwr::k_r_maps, dim3((r->R + 31) / 32, (r->R + 7) / 8, r->tiles), 256, 0, r->stream, r->pdl, ma));
         MW_LAUNCH_CHECK();
     }

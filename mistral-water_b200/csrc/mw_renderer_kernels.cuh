@@ -124,6 +124,9 @@ struct RRowArgs {
 };
 
 // One CTA = two image rows y0, y0 + 1 = 3 packed lines: (hx, hz) of y0, (hx, hz) of y1, (h of y0, h of y1).
+#ifndef MW_RROWS_UNROLL
+#define MW_RROWS_UNROLL 2   // texel batches of the evolve loop in flight (developer switch)
+#endif
 template <int N>
 __global__ void __launch_bounds__(3 * (N / 16)) k_r_rows(const RRowArgs a)
 {
@@ -165,7 +168,8 @@ __global__ void __launch_bounds__(3 * (N / 16)) k_r_rows(const RRowArgs a)
         const float fx = kx * sc, fz = ky * sc;
         F = make_float4(H.y * fx, H.y * fz, -H.x * fx, -H.x * fz);  // (hx.re, hz.re, hx.im, hz.im)
     };
-#pragma unroll 2
+    constexpr int UNR = MW_RROWS_UNROLL;
+#pragma unroll UNR
     for (int x = threadIdx.x; x < N; x += NT) {
         const unsigned o0 = (unsigned)y0 * N + x, o1 = (unsigned)y1 * N + x;
         const float4 s0 = ldg_once4(ini + o0, pol), s1 = ldg_once4(ini + o1, pol);
@@ -221,6 +225,9 @@ struct RColArgs {
     int ab_blocks;         // blockIdx.x < ab_blocks: (hx, hz) slab of W columns; else: h slab of 2 W columns
 };
 
+#ifndef MW_RCOLS_TMA
+#define MW_RCOLS_TMA 1   // (hx, hz) slab by one bulk copy; 0 = 16 per-thread LDG.128 (developer switch, tools/variant builds)
+#endif
 template <int N>
 __global__ void __launch_bounds__(slab_w(N) * (N / 16)) k_r_cols(const RColArgs a)
 {
@@ -233,6 +240,7 @@ __global__ void __launch_bounds__(slab_w(N) * (N / 16)) k_r_cols(const RColArgs 
     float4* tw2 = smem4;
     float2* tw3 = reinterpret_cast<float2*>(smem4 + P::TW2_F4);
     float4* lines = smem4 + P::TW_BYTES / 16;
+    __shared__ uint64_t slab_bar;
 
     const int tile = a.tile0 + blockIdx.y, xt = blockIdx.y;
     const int tid = threadIdx.x;
@@ -244,7 +252,27 @@ __global__ void __launch_bounds__(slab_w(N) * (N / 16)) k_r_cols(const RColArgs 
     mwfft::cpk v[16];
     pdl_trigger();
     pdl_wait();  // the intermediate is k_r_rows' (the predecessor in this stream)
-    if (is_ab) {
+    if (is_ab && MW_RCOLS_TMA) {
+        // the slab is one contiguous block of N * W * 16 bytes in the slab-major intermediate: ONE bulk copy (TMA 1-D form) into
+        // the line buffers, which are free until the first stage writes them -- as in mwk::k_cols_seam; 16 x 512 per-thread
+        // LDG.128 kept the load/store queue full instead (stall reason lg_throttle 9.8, profiles/r02_summary.md)
+        if (tid == 0) mbar_init(&slab_bar, 1);
+        __syncthreads();
+        if (tid == 0) {
+            mbar_expect_tx(&slab_bar, (unsigned)(N * W * sizeof(float4)));
+            bulk_g2s(lines, a.XAB + (size_t)xt * xab_tile_elems(N) + (size_t)blockIdx.x * N * W, (unsigned)(N * W * sizeof(float4)), &slab_bar);
+        }
+        mwfft::load_twiddle_image<N, W * T>(smem4, a.twimg);
+        mbar_wait(&slab_bar, 0);
+        const float4* src = lines + g * W + c;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const float4 e = src[(T * k) * W];
+            v[k].re = make_float2(e.x, e.y);
+            v[k].im = make_float2(e.z, e.w);
+        }
+        __syncthreads();  // everyone has its inputs before the first stage overwrites the raw slab with the lines
+    } else if (is_ab) {
         const float4* src = a.XAB + (size_t)xt * xab_tile_elems(N) + ((size_t)blockIdx.x * N + g) * W + c;
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
@@ -252,6 +280,7 @@ __global__ void __launch_bounds__(slab_w(N) * (N / 16)) k_r_cols(const RColArgs 
             v[k].re = make_float2(e.x, e.y);
             v[k].im = make_float2(e.z, e.w);
         }
+        mwfft::load_twiddle_image<N, W * T>(smem4, a.twimg);
     } else {
         // 16 contiguous bytes = columns b0 + 2c, b0 + 2c + 1 of one row: (re0, im0, re1, im1)
         const float4* src = reinterpret_cast<const float4*>(a.XC + (size_t)xt * plane + ((size_t)(b0 / (2 * W)) * N + g) * (2 * W) + 2 * c);
@@ -261,8 +290,8 @@ __global__ void __launch_bounds__(slab_w(N) * (N / 16)) k_r_cols(const RColArgs 
             v[k].re = make_float2(e.x, e.z);
             v[k].im = make_float2(e.y, e.w);
         }
+        mwfft::load_twiddle_image<N, W * T>(smem4, a.twimg);
     }
-    mwfft::load_twiddle_image<N, W * T>(smem4, a.twimg);
     auto cta_sync = [] { __syncthreads(); };
     mwfft::fft_line_inreg<N, -1>(v, line, g, tw2, tw3, cta_sync);
     if (is_ab) {
@@ -292,7 +321,7 @@ struct RMapArgs {
     float4* white_rgba;  // [tiles][R][R] (xx, xx, xx, 1) as the fragment returns it        or NULL
     float* jacobian;     // [tiles][R][R] (developer / test output)                         or NULL
     int R;
-    int tiles;
+    int tile0;           // first image of this launch (blockIdx.z counts from it)
     int step;            // WhiteCap tap distance in texels = R / mesh resolution (8)
     int repeat;          // 0: clamp at the border (RenderTexture default), 1: repeat
     float texel_size;    // _Length / _Resolution (OceanNormal.shader:42)
@@ -306,7 +335,7 @@ __global__ void __launch_bounds__(256) k_r_maps(const RMapArgs a)
     pdl_trigger();
     pdl_wait();  // the two images are k_r_cols'
     if (x >= R || y >= R) return;
-    const size_t base = (size_t)blockIdx.z * R * R;
+    const size_t base = (size_t)(a.tile0 + blockIdx.z) * R * R;
     const float4* D = a.displacement + base;
     const float4* H = a.height + base;
     auto wrap = [&](int i) { return a.repeat ? (i + R) & (R - 1) : min(max(i, 0), R - 1); };

@@ -319,6 +319,7 @@ int create_rank(mw_tiles* t, TileRank& r, int rank, int device)
     if ((rc = make_event(&r.ev_user))) return rc;
     for (int b = 0; b < 2; ++b)
         if ((rc = make_event(&r.ev_gen[b])) || (rc = make_event(&r.ev_comm[b])) || (rc = make_event(&r.ev_free[b]))) return rc;
+    MW_CUDA(cudaFuncSetAttribute(k_push_slots_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(PUSH_STAGES * t->push_chunk)));
     MW_CUDA(cudaMalloc((void**)&r.alloc, t->alloc_bytes));
     MW_CUDA(cudaMemset(r.alloc + t->flags_off, 0, sizeof(FlagWords)));
     r.gather[0] = reinterpret_cast<float*>(r.alloc);
@@ -702,9 +703,7 @@ int launch_push(mw_tiles* t, int push, cudaStream_t s, const float* src, char* c
         pa.chunk = t->push_chunk;
         pa.bytes = (unsigned long long)slot_bytes;
         for (int i = 0; i < npeers; ++i) pa.dst[i] = dst[i];
-        const size_t smem = (size_t)PUSH_STAGES * t->push_chunk;
-        MW_CUDA(cudaFuncSetAttribute(k_push_slots_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_push_slots_bulk<<<t->push_ctas, 32, smem, s>>>(pa);
+        k_push_slots_bulk<<<t->push_ctas, 32, (size_t)PUSH_STAGES * t->push_chunk, s>>>(pa);   // (attribute set in create_rank)
     }
     MW_LAUNCH_CHECK();
     return MW_OK;
