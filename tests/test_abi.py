@@ -99,6 +99,33 @@ def test_tiles_struct_layouts_match_header(mw):
     assert int(re.search(r"#define MW_TILES_MAX_WORLD (\d+)", hdr).group(1)) == n.MW_TILES_MAX_WORLD
 
 
+def _header_enumerators():
+    """name -> value of every `MW_X = <int or 1u << k>` enumerator in the header"""
+    out = {}
+    for name, val in re.findall(r"\b(MW_[A-Z0-9_]+)\s*=\s*(-?\d+u?\s*(?:<<\s*\d+)?)", _header()):
+        m = re.fullmatch(r"(-?\d+)u?\s*(?:<<\s*(\d+))?", val.strip())
+        out[name] = int(m.group(1)) << int(m.group(2) or 0)
+    return out
+
+
+def test_enumerators_match_header_in_python_and_csharp(mw):
+    """Every status code / flag / gather mode of include/mistral_ocean.h carries the same value in the ctypes mirror, and the
+    ones the C# binding spells out agree too (bindings/MistralOceanNative.cs is source only: nothing here compiles it)."""
+    enums = _header_enumerators()
+    for must in ("MW_E_NCCL", "MW_DEVICE_PTRS", "MW_GATHER_AUTO", "MW_TILES_ASYNC", "MW_TILES_PUSH_CE", "MW_TILES_PUSH_SM", "MW_TILES_PUSH_TMA"):
+        assert must in enums, must
+    n = mw.native
+    for name, val in enums.items():
+        assert hasattr(n, name), f"{name} missing in mistral-water_b200/native.py"
+        assert getattr(n, name) == val, (name, getattr(n, name), val)
+    cs = open(os.path.join(ROOT, "bindings", "MistralOceanNative.cs")).read()
+    spelled = dict((k, int(v)) for k, v in re.findall(r"\b(MW_[A-Z0-9_]+)\s*=\s*(-?\d+)\b", cs))
+    assert {"MW_GATHER_AUTO", "MW_TILES_PUSH_TMA"} <= set(spelled)
+    for name, val in spelled.items():
+        if name in enums:
+            assert enums[name] == val, (name, val, enums[name])
+
+
 def test_no_cpu_fallback_without_a_device(mw):
     """On a box without a GPU the engine must refuse, not compute on the host."""
     import torch
