@@ -50,9 +50,10 @@ def test_world_one_tile_set_equals_single_handle(mw, gather):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("gather", ["peer", "nccl"])
-def test_single_process_drives_two_gpus(mw, gather):
-    """ONE process, no torch.distributed: what a single C# host does (ncclCommInitAll / peer copies fenced by events)."""
+@pytest.mark.parametrize("gather,push", [("peer", "tma"), ("peer", "sm"), ("peer", "ce"), ("nccl", "tma")])
+def test_single_process_drives_two_gpus(mw, gather, push):
+    """ONE process, no torch.distributed: what a single C# host does (ncclCommInitAll / peer pushes fenced by events), with each
+    of the peer arm's push engines (TMA bulk-copy kernel, SM-store kernel, copy engines)."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
@@ -60,7 +61,7 @@ def test_single_process_drives_two_gpus(mw, gather):
     world = 2
     times = [0.0, 1.7, 3.25, 60.0]
     exp = _expected(mw, torch, world, times)
-    with TileSet(N, world, rank=None, devices=[0, 1], tiles_per_rank=TPR, gather=gather, asynchronous=True) as ts:
+    with TileSet(N, world, rank=None, devices=[0, 1], tiles_per_rank=TPR, gather=gather, asynchronous=True, push=push) as ts:
         assert ts.local_ranks == world and ts.gather_impl == gather
         ts.init_spectrum()
         # back-to-back frames with no host synchronisation: frame k's gather overlaps frame k + 1's generation
@@ -83,12 +84,14 @@ def _torchrun(world, extra_env=None):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("world", [2, 4])
-def test_one_process_per_gpu_gathers_match_single_handles(world):
+@pytest.mark.parametrize("world,push", [(2, "tma"), (2, "sm"), (2, "ce"), (4, "tma")])
+def test_one_process_per_gpu_gathers_match_single_handles(world, push):
+    """torchrun: every gathered tile bit-equal to a single-handle run, for the peer arm (with the push engine named; the
+    MW_TILES_PUSH override reaches mw_tiles_create in every rank) and for the ncclAllGather arm."""
     import torch
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
-    r = _torchrun(world)
+    r = _torchrun(world, {"MW_TILES_PUSH": push})
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     assert "TILES_CHECK OK" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
 
