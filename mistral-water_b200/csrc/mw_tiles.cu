@@ -355,6 +355,25 @@ void destroy_rank(mw_tiles* t, TileRank& r)
     r.device = -1;
 }
 
+// cudaDeviceEnablePeerAccess once per ordered pair and process: a second tile set must not raise
+// cudaErrorPeerAccessAlreadyEnabled again (harmless, but every API error shows up in memcheck reports); someone else -- NCCL,
+// the host -- may still have enabled the pair before us.
+int enable_peer_once(int from, int to)
+{
+    static bool enabled[64][64] = {};
+    const bool tracked = from >= 0 && from < 64 && to >= 0 && to < 64;
+    if (tracked && enabled[from][to]) return MW_OK;
+    MW_CUDA(cudaSetDevice(from));
+    const cudaError_t e = cudaDeviceEnablePeerAccess(to, 0);
+    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+        mw_set_error("cudaDeviceEnablePeerAccess(%d -> %d): %s", from, to, cudaGetErrorString(e));
+        return MW_E_CUDA;
+    }
+    (void)cudaGetLastError();
+    if (tracked) enabled[from][to] = true;
+    return MW_OK;
+}
+
 // all local ranks in one process: peer access between every pair of devices
 int connect_single(mw_tiles* t)
 {
@@ -366,13 +385,7 @@ int connect_single(mw_tiles* t)
                     int can = 0;
                     MW_CUDA(cudaDeviceCanAccessPeer(&can, a.device, b.device));
                     if (!can) { mw_set_error("no peer access from device %d to device %d", a.device, b.device); return MW_E_CUDA; }
-                    MW_CUDA(cudaSetDevice(a.device));
-                    const cudaError_t e = cudaDeviceEnablePeerAccess(b.device, 0);
-                    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
-                        mw_set_error("cudaDeviceEnablePeerAccess(%d -> %d): %s", a.device, b.device, cudaGetErrorString(e));
-                        return MW_E_CUDA;
-                    }
-                    (void)cudaGetLastError();
+                    { int rc = enable_peer_once(a.device, b.device); if (rc) return rc; }
                 }
                 for (int k = 0; k < 2; ++k) a.peer_gather[k][b.rank] = b.gather[k];
                 a.peer_flags[b.rank] = b.flags;
