@@ -220,13 +220,14 @@ namespace MistralWater.Native
         public readonly MwTilesLayout layout;
         public readonly IntPtr[] gathered;               // per GPU: [world][slotFloats] floats of the latest frame
 
+        // flags: 0 = blocking calls + the default push engine (TMA bulk copies); MW_TILES_ASYNC and one of MW_TILES_PUSH_* may be or-ed in
         public TileSetEngine(int world, int resolution, float unitWidth, float choppiness, float amplitude, Vector2 wind, ulong seed,
-                             int gather = MistralOcean.MW_GATHER_AUTO)
+                             int gather = MistralOcean.MW_GATHER_AUTO, uint flags = 0)
         {
             var p = new MwTilesParams { ocean = new MwOceanParams { resolution = resolution, unitWidth = unitWidth,
                 length = resolution * unitWidth, choppiness = choppiness, amplitude = amplitude, windX = wind.x, windY = wind.y,
                 tDivision = 1f, seed = seed, tiles = 1 }, world = world, rank = -1, tilesPerRank = 1,
-                gather = gather, devices = new int[16], windStepDeg = 45f };
+                gather = gather, devices = new int[16], windStepDeg = 45f, flags = flags };
             for (int i = 0; i < world; ++i) p.devices[i] = i;
             MistralOcean.Check(MistralOcean.mw_tiles_create(ref p, out handle));
             MistralOcean.Check(MistralOcean.mw_tiles_get_layout(handle, out layout));
