@@ -350,10 +350,33 @@ def run_engine(args):
         barrier()
         return max_over_ranks(e0.elapsed_time(e1))
 
-    def measure_arm(gather):
+    def open_tiles(gather):
+        """The tile set of one gather arm, or None when ANY rank could not set it up (e.g. a box whose containers cannot share CUDA
+        IPC handles): the verdict is all-reduced, so every rank takes the same branch afterwards.  Returns (tiles, error text)."""
+        st, err = None, ""
+        try:
+            st = ShardedTiles(N, rank, world, tiles_per_rank=T, base_seed=1000, device=dev, gather=gather)
+        except Exception as e:  # noqa: BLE001
+            err = f"{type(e).__name__}: {e}"
+        if world > 1:
+            ok = torch.tensor([0 if st is None else 1], device=dev, dtype=torch.int32)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok.item()) == 0:
+                if st is not None:
+                    st.tileset.close()      # no collective teardown: the peers never connected
+                    st.tileset = None
+                return None, err or "another rank failed to set up this arm"
+        elif st is None:
+            raise RuntimeError(err)
+        return st, ""
+
+    def measure_arm(gather, st=None):
         """One gather arm at world > 1 (or the plain engine at world == 1): the timed step, then compute alone and the
         gather alone.  Rank-uniform control flow throughout: K, W and the leg order are the same on every rank."""
-        st = ShardedTiles(N, rank, world, tiles_per_rank=T, base_seed=1000, device=dev, gather=gather)
+        if st is None:
+            st, err = open_tiles(gather)
+            if st is None:
+                return None, {"impl": gather, "unavailable": err}
         step = (lambda k: st.generate_pipelined(0.016 * k)) if world > 1 else (lambda k: st.generate_local(0.016 * k))
         res = {"impl": st.gather_impl}
         with torch.cuda.stream(st.stream):
@@ -388,6 +411,13 @@ def run_engine(args):
         return st, res
 
     st, main = measure_arm("auto")     # MW_GATHER_AUTO: the peer pushes (include/mistral_ocean.h)
+    auto_fallback = None
+    if st is None:
+        # the default arm could not be set up on this box: the step is measured with ncclAllGather instead, and the line says so
+        auto_fallback = main["unavailable"]
+        st, main = measure_arm("nccl")
+        if st is None:
+            raise RuntimeError(f"neither gather arm could be set up: {auto_fallback}; {main['unavailable']}")
     ms, compute_ms, clocks, launches = main["ms"], main["compute_ms"], main["clocks"], main["launches"]
     value = world * pts_rank * K / (ms * 1e-3)
     stream = st.stream
@@ -448,8 +478,12 @@ def run_engine(args):
     if world > 1:
         st.close()
         barrier()
-        st2, other = measure_arm("nccl" if main["impl"] == "peer" else "peer")
-        st2.close()
+        if auto_fallback is None:
+            st2, other = measure_arm("nccl" if main["impl"] == "peer" else "peer")
+            if st2 is not None:
+                st2.close()
+        else:
+            other = {"impl": "peer", "unavailable": auto_fallback}
         barrier()
         st, _ = None, None
 
@@ -485,7 +519,7 @@ def run_engine(args):
     else:
         # the tile set: every step uploads this rank's h0 from pinned host memory, generates, ALL-GATHERS, and downloads this
         # rank's slot of the gathered buffer once the gather has completed (the hosts fetch each tile once, over N PCIe links)
-        st3 = ShardedTiles(N, rank, world, tiles_per_rank=T, base_seed=1000, device=dev, gather="auto")
+        st3 = ShardedTiles(N, rank, world, tiles_per_rank=T, base_seed=1000, device=dev, gather=main["impl"])   # the arm `value` was measured with
         ts = st3.tileset
         h0, h0c = pin(pts_rank, 2), pin(pts_rank, 2)
         d_h0 = [torch.empty(pts_rank, 2, device=dev) for _ in range(2)]      # upload staging, double-buffered
@@ -587,8 +621,10 @@ def run_engine(args):
                 "ingress_floor_note": f"every rank must RECEIVE (world - 1) x {slot_bytes / 1e6:.1f} MB per step through its NVLink "
                                       f"ingress: {NVLINK_NOMINAL_GBS:.0f} GB/s nominal, {NVLINK_PEER_COPY_GBS:.0f} GB/s measured peer copy",
                 "value_ceiling_at_floor": world * pts_rank / (max(floor_nom, compute_ms / K) * 1e-3),
-                "arms": {main["impl"]: arm(main), other["impl"]: arm(other)},
+                "arms": {main["impl"]: arm(main), other["impl"]: (arm(other) if "unavailable" not in other else other)},
                 "default_arm": main["impl"], "default_arm_rule": "MW_GATHER_AUTO: peer-memory pushes (TMA bulk-copy kernel) at every world size; ncclAllGather if peer memory is unusable",
+                **({"default_arm_fallback": f"the peer arm could not be set up on this box ({auto_fallback}); `value` is the ncclAllGather arm's"}
+                   if auto_fallback else {}),
                 "rank0_numa_binding": numa,
             }
         emit(line)

@@ -598,6 +598,10 @@ extern "C" int mw_tiles_connect(mw_tiles* t, const void* blobs)
         return MW_OK;
     }
     MemOps* m = memops();
+    if (getenv("MW_TILES_FAIL_PEER_CONNECT")) {   // developer knob: lets a host rehearse its fallback to the NCCL arm
+        mw_set_error("mw_tiles_connect: peer mappings refused (MW_TILES_FAIL_PEER_CONNECT is set)");
+        return MW_E_CUDA;
+    }
     for (int p = 0; p < t->world; ++p) {
         if (p == r.rank) continue;
         int can = 0;
