@@ -178,3 +178,71 @@ def test_stockham_pass_count_matches_ocean_renderer(r64):
     finally:
         r64.stockham_stage = orig
     assert [c[0] for c in calls] == [2, 4, 8, 16] * 2 and [c[1] for c in calls] == [-1] * 4 + [-2] * 4
+
+
+# ---------------------------------------------------------------- closed forms derived from the C# source, not from the oracle
+def _plane_wave_closed_form(N, L, uw, chop, modes, t):
+    """FFTMesh.cs:192-276 evaluated by hand for a spectrum with a handful of non-zero entries, in float64.
+
+    modes = [(n, m, h0 (complex), h0conj (complex))].  For one entry, htilde = h0 e^{i w t} + h0conj e^{-i w t} (:178-190) and the
+    double loop of Displacement (:199-217) has a single term: with phi = kx x + kz z,
+        c      = htilde e^{i phi}
+        height = Re c                                   (:210, :219)
+        n     += (-kx Im c, 0, -kz Im c)  ->  normal = normalize((kx Im c, 1, kz Im c))   (:211, :218)
+        d     += (kx / |k| Im c, -kz / |k| Im c)        (:214)
+    so hds = d, vertMeow = (x - d.x chop, height, z - d.y chop) (:243-247); then the forward differences of :253-273."""
+    half = N // 2
+    off = uw / 2.0 if N % 2 == 0 else 0.0
+    ax = (np.arange(N) - half) * uw + off                       # :107-112
+    X, Z = np.meshgrid(ax, ax, indexing="ij")                   # index = i * N + j, i <-> x, j <-> z
+    height = np.zeros((N, N)); dx = np.zeros((N, N)); dz = np.zeros((N, N)); sx = np.zeros((N, N)); sz = np.zeros((N, N))
+    w0 = 2.0 * np.pi / L
+    for n, m, h0, hc in modes:
+        kx = 2.0 * np.pi * (n - N / 2.0) / L                    # :201, :204
+        kz = 2.0 * np.pi * (m - N / 2.0) / L
+        kl = np.hypot(kx, kz)
+        om = np.floor(np.sqrt(9.81 * kl) / w0) * w0             # :141-147
+        c = (h0 * np.exp(1j * om * t) + hc * np.exp(-1j * om * t)) * np.exp(1j * (kx * X + kz * Z))
+        height += c.real
+        sx += kx * c.imag; sz += kz * c.imag                   # nor = normalize(up - n), n = (-kx Im c, 0, -kz Im c)
+        if kl >= 1e-4:                                          # :212
+            dx += kx / kl * c.imag; dz += -kz / kl * c.imag
+    inv = 1.0 / np.sqrt(sx * sx + 1.0 + sz * sz)
+    normal = np.stack([sx * inv, inv, sz * inv], -1)
+    vert = np.stack([X - dx * chop, height, Z - dz * chop], -1)
+    ddx = np.zeros((N, N, 2)); ddy = np.zeros((N, N, 2))
+    hds = np.stack([dx, dz], -1)
+    ddx[:-1] = 0.5 * (hds[:-1] - hds[1:])                       # :260-263 (index + resolution = next i)
+    ddy[:, :-1] = 0.5 * (hds[:, :-1] - hds[:, 1:])              # :264-267 (index + 1 = next j)
+    jac = (1 + ddx[..., 0]) * (1 + ddy[..., 1]) - ddx[..., 1] * ddy[..., 0]
+    noise = 0.3 * np.hypot(normal[..., 0], normal[..., 2])      # :269
+    turb = np.maximum(1.0 - jac + noise, 0.0)
+    s = np.clip(turb, 0.0, 1.0)
+    white = s * s * (3.0 - 2.0 * s)                             # Mathf.SmoothStep(0, 1, turb), :273
+    return {"vertMeow": vert.reshape(-1, 3), "normals": normal.reshape(-1, 3), "hds": hds.reshape(-1, 2), "jacobian": jac.reshape(-1),
+            "whitecap": white.reshape(-1)}
+
+
+@pytest.mark.parametrize("t", [0.0, 1.7, 60.0])
+@pytest.mark.parametrize("modes", [
+    [(20, 11, 0.35 - 0.2j, 0.0)],                                           # one travelling wave
+    [(20, 11, 0.0, 0.25 + 0.4j)],                                           # only the conjugate partner: e^{-i w t}
+    [(9, 25, 0.3 + 0.1j, -0.2 + 0.15j), (16, 16, 0.5 + 0.0j, 0.1 - 0.1j), (31, 0, -0.15 + 0.2j, 0.05j)],   # a sum, incl. k = 0
+], ids=["h0", "h0conj", "three-modes-with-dc"])
+def test_literal_oracle_against_closed_form_plane_waves(cref, modes, t):
+    """The oracle's EvaluateWaves against a derivation made by hand from FFTMesh.cs for spectra with 1-3 non-zero entries: every
+    output (displaced vertex, normal, hds, Jacobian, whitecap) in closed form.  Catches a mis-restated sign, index order (i <-> x),
+    dispersion, conjugate term or forward-difference direction, which the oracle-vs-oracle fixtures cannot."""
+    N = 32
+    p = cref.params(N, choppiness=0.8)
+    v, _, _ = cref.generate_mesh(p, seed=1)
+    h0 = np.zeros((N * N, 2), np.float32); hc = np.zeros((N * N, 2), np.float32)
+    for n, m, a, b in modes:
+        h0[n * N + m] = (np.real(a), np.imag(a)); hc[n * N + m] = (np.real(b), np.imag(b))
+    got = cref.evaluate_waves(p, v, h0, hc, t, threads=2)
+    want = _plane_wave_closed_form(N, float(p.length), float(p.unit_width), 0.8, modes, t)
+    # fp32 phases: |k.x| reaches ~100 rad and w t ~200 rad at t = 60 (one ulp of the angle is ~1e-5), amplitudes are O(1)
+    tol = 2e-4 if t > 10 else 5e-5
+    for key in ("vertMeow", "normals", "hds", "jacobian"):
+        assert max_abs(got[key], want[key]) < tol, (key, max_abs(got[key], want[key]))
+    assert max_abs(got["colors"][:, 0], want["whitecap"]) < 4 * tol
