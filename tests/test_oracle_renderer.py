@@ -123,3 +123,75 @@ def test_golden_renderer_fixture():
         m = s.generate_texture(float(g["dt"]))
     for k in ("displacement", "height", "normal", "white", "phase"):
         assert np.allclose(m[k], g[k], rtol=0, atol=1e-6 * max(1.0, float(np.abs(g[k]).max()))), k
+
+
+# ---------------------------------------------------------------- a closed form derived from the shader sources, not from the oracle
+def _single_mode_frame(res, length, chop, mult, dt, x0, y0, a, b):
+    """OceanRenderer.GenerateTexture for an initial image with ONE non-zero texel (x0, y0) = (h0, h0conj) = (a, b), first frame
+    (phase images start black), repeat wrap, all in float64 and in closed form:
+      Dispersion.shader:37-40 + FFTCommon.cginc:101-114   phi = fmod(sqrt(G |k| (1 + |k|^2 / 370^2)) dt mult, 2 PI)
+      Spectrum.shader:45-50                               h = a e^{i phi} + b e^{-i phi};  hx = -i h kx / w chop;  hz = -i h kz / w chop
+      Stockham.shader + OceanRenderer.cs:229-298          forward-sign, un-normalised 2-D DFT: one texel -> a plane wave
+      OceanNormal.shader:32-56, WhiteCap.shader:33-45     stencils of that plane wave (taps 1 texel / 8 texels apart)."""
+    R_ = 8 * res
+    PI, G = 3.1415926536, 9.81
+    nx = x0 if x0 < R_ / 2 else x0 - R_                      # GetWave, FFTCommon.cginc:58-67 (after its n -= 0.5)
+    ny = y0 if y0 < R_ / 2 else y0 - R_
+    kx, kz = 2 * PI * nx / length, 2 * PI * ny / length
+    kl = np.hypot(kx, kz)
+    phi = np.fmod(np.sqrt(G * kl * (1 + kl * kl / 370 / 370)) * dt * mult, 2 * PI)
+    h = a * np.exp(1j * phi) + b * np.exp(-1j * phi)
+    w = max(1e-4, kl)
+    hx, hz = -1j * h * kx / w * chop, -1j * h * kz / w * chop
+    Y, X = np.meshgrid(np.arange(R_), np.arange(R_), indexing="ij")      # images are [y][x]
+
+    def plane(c, dx=0, dy=0):
+        return c * np.exp(-2j * np.pi * (x0 * (X + dx) + y0 * (Y + dy)) / R_)
+
+    Dx, Dz, H = plane(hx), plane(hz), plane(h)
+    disp = np.stack([Dx.real, Dx.imag, Dz.real, Dz.imag], -1)
+    height = np.stack([H.real, H.imag, H.real, H.imag], -1)
+    ts = length / R_
+    centre = np.stack([Dx.real, Dx.imag, Dz.real], -1)                  # disp.rgb "as written" (:44)
+
+    def vec(dx, dy):                                                    # GetVec :32-37 = (disp.r, height.r, disp.b)
+        return np.stack([plane(hx, dx, dy).real, plane(h, dx, dy).real, plane(hz, dx, dy).real], -1)
+
+    right = np.array([ts, 0, 0]) + vec(1, 0) - centre
+    left = np.array([-ts, 0, 0]) + vec(-1, 0) - centre
+    top = np.array([0, 0, -ts]) + vec(0, -1) - centre
+    bottom = np.array([0, 0, ts]) + vec(0, 1) - centre
+    s = np.cross(right, top) + np.cross(top, left) + np.cross(left, bottom) + np.cross(bottom, right)
+    n = s / np.linalg.norm(s, axis=-1, keepdims=True)
+    st = R_ // res                                                       # 1 / _Length in uv, _Length = resolution (:306) -> 8 texels
+
+    def rb(dx, dy):
+        return np.stack([plane(hx, dx, dy).real, plane(hz, dx, dy).real], -1)
+
+    ddy = -0.5 * (rb(0, -st) - rb(0, st)) / 8
+    ddx = -0.5 * (rb(-st, 0) - rb(st, 0)) / 8
+    jac = (1 + ddx[..., 0]) * (1 + ddy[..., 1]) - ddx[..., 1] * ddy[..., 0]
+    turb = np.maximum(0, 1 - jac + 0.3 * np.hypot(n[..., 0], n[..., 2]))
+    c = np.clip(turb, 0, 1)
+    return {"displacement": disp, "height": height, "normal": np.concatenate([n, np.ones_like(n[..., :1])], -1),
+            "white": c * c * (3 - 2 * c), "jacobian": jac, "phase_at_mode": phi}
+
+
+@pytest.mark.parametrize("x0,y0,a,b", [(3, 5, 0.2 - 0.1j, 0.0), (29, 2, 0.0, 0.15 + 0.2j), (6, 27, 0.1 + 0.2j, -0.2 + 0.05j)],
+                         ids=["h0", "h0conj-negative-kx", "both-negative-kz"])
+def test_single_mode_frame_against_the_closed_form(x0, y0, a, b):
+    """The whole chain -- phase step, spectra, 2 x log2(R) Stockham blits per axis, normal and whitecap stencils -- for a spectrum
+    with one non-zero texel, against the plane wave it must produce.  Catches a wrong DFT sign, a transposed image, a mis-packed
+    channel, the sign of -MultByI, the FFT-ordered wave vector and the tap distances, none of which oracle-vs-oracle fixtures see."""
+    res, length, chop, mult, dt = 4, 40.0, 1.3, 2.0, 0.5      # dt * mult is formed in fp32 (OceanRenderer.cs:223): keep it exact
+    Rr = 8 * res
+    ini = np.zeros((Rr, Rr, 4), F32)
+    ini[y0, x0] = (a.real, a.imag, np.real(b), np.imag(b))
+    a32, b32 = complex(*ini[y0, x0, :2]), complex(*ini[y0, x0, 2:])       # what the image really holds (fp32-rounded)
+    want = _single_mode_frame(res, length, chop, mult, dt, x0, y0, a32, b32)
+    st = R.RendererState(res, length, chop, 1.0, (1.0, 0.0), 0.0, 0.0, mult=mult, dtype=F64, wrap="repeat", initial=ini)
+    got = st.generate_texture(dt)
+    assert abs(got["phase"][y0, x0] - want["phase_at_mode"]) < 1e-12
+    for k in ("displacement", "height", "normal", "white", "jacobian"):
+        assert np.abs(got[k] - want[k]).max() < 2e-9, (k, np.abs(got[k] - want[k]).max())   # the shader's 11-digit PI in the twiddles
+    assert np.abs(want["displacement"]).max() > 5e-2 and np.ptp(want["white"]) > 1e-3           # the case is not degenerate
