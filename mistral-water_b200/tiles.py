@@ -77,6 +77,9 @@ class TileSet:
                 torch.distributed -- what a single C# host process does.
     rank=r    : one process per GPU; `exchange(blob) -> [blob of rank 0, blob of rank 1, ...]` is any all-gather of
                 512-byte strings the host has (ShardedTiles passes torch.distributed.all_gather_object).
+    gather    : "auto" (the peer pushes; include/mistral_ocean.h MW_GATHER_AUTO), "peer", "nccl".
+    push      : what moves a slot into the peers' buffers in the peer arm -- "tma" (bulk-copy kernel, default), "sm" (store kernel),
+                "ce" (copy engines): the MW_TILES_PUSH_* flags.
     """
 
     def __init__(self, N: int, world: int, rank: int | None = None, devices=None, tiles_per_rank: int = 1,
