@@ -246,3 +246,22 @@ def test_literal_oracle_against_closed_form_plane_waves(cref, modes, t):
     for key in ("vertMeow", "normals", "hds", "jacobian"):
         assert max_abs(got[key], want[key]) < tol, (key, max_abs(got[key], want[key]))
     assert max_abs(got["colors"][:, 0], want["whitecap"]) < 4 * tol
+
+
+@pytest.mark.parametrize("N,L", [(12, 12.39), (13, 13.0)], ids=["fft-mesh-demo-scene", "odd-grid"])
+def test_literal_oracle_against_closed_form_off_the_transform_grid(cref, N, L):
+    """The same closed form on the grids the direct-sum path serves (the FFT Mesh scene's own resolution 12 / length 12.39,
+    FFT Mesh.unity:147,150, and an odd grid, whose rest positions carry no half-cell offset, FFTMesh.cs:112): the sum is literal,
+    so no periodicity is needed for the closed form to hold."""
+    modes = [(2, 9, 0.3 + 0.1j, -0.2 + 0.15j), (N // 2, N // 2, 0.4 + 0.0j, 0.0), (N - 1, 0, -0.15 + 0.2j, 0.05j)]
+    p = cref.params(N, length=L, choppiness=1.0)
+    v, _, _ = cref.generate_mesh(p, seed=1)
+    h0 = np.zeros((N * N, 2), np.float32); hc = np.zeros((N * N, 2), np.float32)
+    for n, m, a, b in modes:
+        h0[n * N + m] = (np.real(a), np.imag(a)); hc[n * N + m] = (np.real(b), np.imag(b))
+    for t in (0.0, 1.7):
+        got = cref.evaluate_waves(p, v, h0, hc, t, threads=1)
+        want = _plane_wave_closed_form(N, L, 1.0, 1.0, modes, t)
+        for key in ("vertMeow", "normals", "hds", "jacobian"):
+            assert max_abs(got[key], want[key]) < 5e-5, (key, t, max_abs(got[key], want[key]))
+        assert max_abs(got["colors"][:, 0], want["whitecap"]) < 2e-4
